@@ -1,0 +1,67 @@
+"""Experiment configuration — same keys and semantics as the reference's `config.py:25-76`.
+
+Extra keys (all optional, defaults reproduce the B200 benchmark configuration):
+  dtype           "bf16" | "fp16" | "fp32": autocast dtype used when `use_amp` is True
+  channels_last   run the network in NHWC (what cuDNN's Blackwell kernels and the SyncBN kernels want)
+  synthetic       train on synthetic batches of the dataloader's output contract (no dataset on this machine)
+"""
+import os
+from collections import OrderedDict
+
+__all__ = ["user_config"]
+
+proj_root = os.path.dirname(os.path.abspath(__file__))
+datasets_root = os.environ.get("SOD_DATASETS_ROOT", "/home/lart/Datasets/")
+
+_rgb = os.path.join(datasets_root, "Saliency/RGBSOD")
+ecssd_path = os.path.join(_rgb, "ECSSD")
+dutomron_path = os.path.join(_rgb, "DUT-OMRON")
+hkuis_path = os.path.join(_rgb, "HKU-IS")
+pascals_path = os.path.join(_rgb, "PASCAL-S")
+soc_path = os.path.join(_rgb, "SOC/Test")
+dutstr_path = os.path.join(_rgb, "DUTS/Train")
+dutste_path = os.path.join(_rgb, "DUTS/Test")
+
+user_config = {
+    "model": "cp_res50",
+    "resume_mode": "",            # ['train', 'test', '']
+    "version": "0.2",
+    "use_aux_loss": True,
+    "save_pre": True,
+    "epoch_num": 30,
+    "lr": 0.05,
+    "xlsx_name": "result_full.xlsx",
+    "output_name": "output",
+    "is_distributed": True,
+    "use_amp": True,
+    "rgb_data": {
+        "tr_data_path": dutstr_path,
+        "val_data_path": {"pascal-s": pascals_path},
+        "te_data_list": OrderedDict({"pascal-s": pascals_path, "ecssd": ecssd_path, "dut-omron": dutomron_path,
+                                     "hku-is": hkuis_path, "duts": dutste_path, "soc": soc_path}),
+    },
+    "record_freq": 100,
+    "print_freq": 10,
+    "val_freq": 5,
+    "save_freq": 5,
+    "prefix": (".jpg", ".png"),
+    "size_list": None,            # e.g. [256, 320, 384] for multi-scale training
+    "reduction": "mean",
+    "optim": "f3_trick",
+    "weight_decay": 5e-4,
+    "momentum": 0.9,
+    "nesterov": False,
+    "sche_usebatch": False,
+    "lr_type": "poly",
+    "warmup_epoch": 1,
+    "lr_decay": 0.9,
+    "batch_size": 48,
+    "num_workers": 4,
+    "input_size": 320,
+    "proj_root": proj_root,
+    # --- B200 engine extras ---
+    "dtype": "bf16",
+    "channels_last": True,
+    "synthetic": True,
+    "synthetic_iters_per_epoch": 20,
+}

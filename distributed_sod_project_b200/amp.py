@@ -1,0 +1,82 @@
+"""amp seam: `amp.initialize`, `amp.scale_loss`, `amp.state_dict/load_state_dict` of the reference
+(apex.amp O1; train.py:15,181-183,298-300, utils/pipeline_ops.py:74,121).
+
+B200 default: bf16 autocast, loss scale fixed at 1.0 — bf16 has fp32's exponent range, so the dynamic
+scaler of apex O1 has nothing to do; weights, gradients and optimizer state stay fp32 ("fp32 master") exactly
+as under O1.  `dtype=torch.float16` keeps apex's dynamic-scale behaviour (init 2^16, ÷2 and skip the step on
+overflow, ×2 every 2000 clean steps): the unscale factor and the overflow flag are consumed INSIDE the fused
+optimizer kernel, the only extra work is one read of the gradients by `sod_grad_nonfinite`.
+"""
+from __future__ import annotations
+
+import contextlib
+import functools
+
+import torch
+
+from . import _lib
+from .optim import FusedSGD
+
+_cfg = {"enabled": False, "dtype": torch.bfloat16, "scale": 1.0, "dynamic": False, "good_steps": 0,
+        "growth_interval": 2000, "found_inf": None}
+
+
+def initialize(model, optimizer=None, opt_level: str = "O1", dtype: torch.dtype = torch.bfloat16, **_ignored):
+    """Returns (model, optimizer) like apex. The model's forward runs under autocast(dtype)."""
+    if opt_level not in ("O0", "O1"):
+        raise _lib.SodError(f"opt_level {opt_level!r}: only O0/O1 semantics are provided")
+    _cfg["enabled"] = opt_level == "O1"
+    _cfg["dtype"] = dtype
+    _cfg["dynamic"] = _cfg["enabled"] and dtype == torch.float16
+    _cfg["scale"] = 65536.0 if _cfg["dynamic"] else 1.0
+    if _cfg["enabled"]:
+        inner = model.forward
+
+        @functools.wraps(inner)
+        def autocast_forward(*a, **k):
+            with torch.autocast("cuda", dtype=_cfg["dtype"]):
+                return inner(*a, **k)
+
+        model.forward = autocast_forward
+    return (model, optimizer) if optimizer is not None else model
+
+
+@contextlib.contextmanager
+def scale_loss(loss, optimizer):
+    """`with amp.scale_loss(loss, optimizer) as scaled: scaled.backward()` (reference train.py:299)."""
+    if not _cfg["dynamic"]:
+        yield loss
+        return
+    if not isinstance(optimizer, FusedSGD):
+        raise _lib.SodError("fp16 dynamic loss scaling is wired into FusedSGD only")
+    scale = _cfg["scale"]
+    yield loss * scale
+    flat = optimizer.flat
+    if _cfg["found_inf"] is None:
+        _cfg["found_inf"] = torch.zeros(1, dtype=torch.int32, device=flat.grad.device)
+    finf = _cfg["found_inf"]
+    finf.zero_()
+    rc = _lib.lib().sod_grad_nonfinite(flat.grad.data_ptr(), flat.numel, finf.data_ptr(), _lib.stream_ptr())
+    _lib.check(rc, "sod_grad_nonfinite")
+    _lib.count_launch()
+    if flat.arena is not None:
+        torch.distributed.all_reduce(finf, op=torch.distributed.ReduceOp.MAX)   # identical verdict on all ranks
+    optimizer.inv_scale = 1.0 / scale
+    optimizer.found_inf = finf
+    if int(finf.item()):                       # apex syncs here too
+        _cfg["scale"] = max(scale / 2.0, 1.0)
+        _cfg["good_steps"] = 0
+    else:
+        _cfg["good_steps"] += 1
+        if _cfg["good_steps"] % _cfg["growth_interval"] == 0:
+            _cfg["scale"] = scale * 2.0
+
+
+def state_dict():
+    return {"loss_scaler0": {"loss_scale": _cfg["scale"], "unskipped": _cfg["good_steps"]}}
+
+
+def load_state_dict(sd):
+    s = sd.get("loss_scaler0", {})
+    _cfg["scale"] = float(s.get("loss_scale", _cfg["scale"]))
+    _cfg["good_steps"] = int(s.get("unskipped", 0))

@@ -1,0 +1,259 @@
+"""Optimizer seam: `make_optimizer`, `CustomScheduler`, and `FusedSGD` (csrc/sgd.cu underneath).
+
+Reference surface kept (paths in the reference repo):
+* `make_optimizer(model, optimizer_type, optimizer_info)`          — utils/pipeline_ops.py:235-316
+  (`sgd_trick`, `sgd_r3`, `sgd_all`, `f3_trick` → FusedSGD; `adam` → torch.optim.Adam, not on the hot path)
+* `CustomScheduler(optimizer, total_num, scheduler_type, scheduler_info).step(optimizer, curr_epoch)`
+                                                                     — utils/pipeline_ops.py:185-232
+* the `torch.optim.Optimizer` protocol the loop relies on: `.param_groups[i]["lr"]` mutated from outside,
+  `.zero_grad()`, `.step()`, `.state_dict()/.load_state_dict()` with per-parameter `momentum_buffer`
+  (utils/pipeline_ops.py:73,118), `str(optimizer)` (train.py:176).
+
+FusedSGD keeps parameters, gradients and momentum in three flat fp32 buffers laid out group-major
+([group 0 | group 1 | … | parameters in no group]); every `p.data` / `p.grad` is a view into them.  `step()`
+is one kernel: world 1 → `sod_sgd_momentum`; world > 1 (after `DistributedDataParallel` has moved the flat
+parameter and gradient buffers into symmetric memory) → `sod_allreduce_sgd`, which also does the
+gradient averaging, so nothing else runs between backward and the next forward.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.optim import Adam, Optimizer
+
+from . import _lib
+
+flat_registry: dict = {}   # id(param) → FlatParams (lets DistributedDataParallel find the optimizer's layout)
+
+_ALIGN = 64  # elements; keeps every tensor view 256-byte aligned and every segment float4-aligned
+
+
+class FlatParams:
+    """Group-major flat storage for a set of parameters."""
+
+    def __init__(self, groups: list[list[nn.Parameter]], leftovers: list[nn.Parameter]):
+        self.groups, self.leftovers = groups, leftovers
+        all_params = [p for g in groups for p in g] + leftovers
+        if not all_params:
+            raise ValueError("no parameters")
+        dev = all_params[0].device
+        if any(p.device != dev or p.dtype != torch.float32 for p in all_params):
+            raise _lib.SodError("FusedSGD needs fp32 parameters on one device")
+        self.device = dev
+        self.slots: list[tuple[nn.Parameter, int]] = []      # (param, element offset)
+        self.ranges: list[tuple[int, int]] = []               # per group [begin, end), then leftovers
+        off = 0
+        for bucket in [*groups, leftovers]:
+            begin = off
+            for p in bucket:
+                self.slots.append((p, off))
+                off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+            self.ranges.append((begin, off))
+        self.numel = off
+        self.param = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.mom = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.arena = None          # set by DistributedDataParallel when world > 1
+        self.param_off = self.grad_off = 0
+        self._bind(copy_from_params=True)
+
+    @staticmethod
+    def _view(buf: torch.Tensor, off: int, p: torch.Tensor) -> torch.Tensor:
+        """view of buf[off:off+numel] with p's shape AND memory format (channels-last conv weights keep their
+        KRSC physical order, so cuDNN's NHWC kernels need no per-iteration weight transpose)"""
+        flat = buf[off:off + p.numel()]
+        if p.dim() == 4 and not p.is_contiguous() and p.is_contiguous(memory_format=torch.channels_last):
+            n, c, h, w = p.shape
+            return flat.view(n, h, w, c).permute(0, 3, 1, 2)
+        return flat.view(p.shape)
+
+    def _bind(self, copy_from_params: bool):
+        with torch.no_grad():
+            for p, off in self.slots:
+                view = self._view(self.param, off, p.data)
+                if copy_from_params:
+                    view.copy_(p.data)
+                g = self._view(self.grad, off, p.data)
+                p.data = view
+                p.grad = g
+
+    def relocate(self, arena, param_off: int, grad_off: int):
+        """Move the flat parameter / gradient buffers into a symmetric arena (momentum stays local)."""
+        new_p = arena.view(param_off, self.numel, torch.float32)
+        new_g = arena.view(grad_off, self.numel, torch.float32)
+        new_p.copy_(self.param)
+        new_g.copy_(self.grad)
+        self.param, self.grad = new_p, new_g
+        self.arena, self.param_off, self.grad_off = arena, param_off, grad_off
+        self._bind(copy_from_params=False)
+
+    def momentum_view(self, p: nn.Parameter) -> torch.Tensor:
+        for q, off in self.slots:
+            if q is p:
+                return self._view(self.mom, off, p.data)
+        raise KeyError("parameter not managed")
+
+
+class FusedSGD(Optimizer):
+    """SGD with momentum / weight decay as one flat sm_100a kernel; gradient averaging folded in when
+    distributed.  Arithmetic = torch.optim.SGD (torch/optim/sgd.py:343-380) with dampening 0, nesterov False."""
+
+    def __init__(self, params, lr=1e-3, momentum=0.0, weight_decay=0.0, nesterov=False, model: nn.Module | None = None):
+        if nesterov:
+            raise _lib.SodError("nesterov momentum is not on the reference's hot path (config.py:65 nesterov=False)")
+        defaults = dict(lr=lr, momentum=momentum, weight_decay=weight_decay, nesterov=False, dampening=0)
+        super().__init__(params, defaults)
+        if len(self.param_groups) > _lib.SOD_MAX_SEGMENTS - 1:
+            raise _lib.SodError(f"at most {_lib.SOD_MAX_SEGMENTS - 1} parameter groups")
+        grouped = {id(p) for g in self.param_groups for p in g["params"]}
+        leftovers = [p for p in model.parameters() if id(p) not in grouped] if model is not None else []
+        self.flat = FlatParams([list(g["params"]) for g in self.param_groups], leftovers)
+        for p, _ in self.flat.slots:
+            flat_registry[id(p)] = self.flat
+        self.inv_scale = 1.0                   # amp: 1/S for the coming step
+        self.found_inf: torch.Tensor | None = None  # amp: device uint32 flag, or None
+        self._grads_clean = True
+        self._clean_version = self.flat.grad._version
+        self._stepped = False
+        self.steps = 0
+
+    # -- torch.optim.Optimizer protocol -------------------------------------------------------------------
+    def zero_grad(self, set_to_none: bool = False):
+        """One memset of the flat gradient buffer (a no-op right after a fused step, which already cleared it).
+        Gradients stay bound as views — `set_to_none` is accepted and ignored."""
+        # the fused step clears the buffer in-kernel; autograd's in-place accumulation bumps the (shared)
+        # version counter of the flat buffer, so an unchanged version means nothing has written since
+        if not (self._grads_clean and self.flat.grad._version == self._clean_version):
+            self.flat.grad.zero_()
+        self._grads_clean = False
+        # autograd may have replaced a .grad (e.g. after an external `p.grad = None`): rebind
+        for p, off in self.flat.slots:
+            if p.grad is None or p.grad.data_ptr() != self.flat.grad.data_ptr() + 4 * off:
+                p.grad = FlatParams._view(self.flat.grad, off, p.data)
+
+    def _segments(self):
+        segs = (_lib.sod_sgd_segment * (len(self.param_groups) + 1))()
+        n = 0
+        for g, (b, e) in zip(self.param_groups, self.flat.ranges):
+            if e > b:
+                segs[n] = _lib.sod_sgd_segment(b, e, float(g["lr"]), float(g["weight_decay"]), float(g["momentum"]), 0)
+                n += 1
+        b, e = self.flat.ranges[-1]
+        if e > b:
+            segs[n] = _lib.sod_sgd_segment(b, e, 0.0, 0.0, 0.0, _lib.SOD_SEG_FROZEN)
+            n += 1
+        return segs, n
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        if closure is not None:
+            raise _lib.SodError("closures are not supported by the fused step")
+        f = self.flat
+        if not f.param.is_cuda:
+            raise _lib.SodError("FusedSGD.step needs CUDA parameters (no CPU fallback)")
+        segs, n = self._segments()
+        finf = self.found_inf.data_ptr() if self.found_inf is not None else None
+        if f.arena is None:
+            rc = _lib.lib().sod_sgd_momentum(f.param.data_ptr(), f.mom.data_ptr(), f.grad.data_ptr(), f.numel, segs, n,
+                                             float(self.inv_scale), finf, _lib.SOD_SGD_ZERO_GRAD, _lib.stream_ptr())
+            _lib.check(rc, "sod_sgd_momentum")
+        else:
+            a = f.arena
+            rc = _lib.lib().sod_allreduce_sgd(a.ref, f.grad_off, f.param_off, f.mom.data_ptr(), f.numel, segs, n,
+                                              float(self.inv_scale), finf, a.next_seq(0), _lib.SOD_SGD_ZERO_GRAD,
+                                              _lib.stream_ptr())
+            _lib.check(rc, "sod_allreduce_sgd")
+        _lib.count_launch()
+        self._grads_clean = True
+        self._clean_version = self.flat.grad._version
+        self._stepped = True
+        self.steps += 1
+
+    # momentum lives in the flat buffer; expose torch.optim.SGD's state layout on demand
+    def state_dict(self):
+        self.state.clear()
+        if self._stepped:
+            for g in self.param_groups:
+                for p in g["params"]:
+                    self.state[p] = {"momentum_buffer": self.flat.momentum_view(p).clone()}
+        sd = super().state_dict()
+        self.state.clear()
+        return sd
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        loaded = False
+        with torch.no_grad():
+            for g in self.param_groups:
+                for p in g["params"]:
+                    buf = self.state.get(p, {}).get("momentum_buffer")
+                    if buf is not None:
+                        self.flat.momentum_view(p).copy_(buf)
+                        loaded = True
+        self.state.clear()
+        self._stepped = self._stepped or loaded
+
+    def __repr__(self):
+        return super().__repr__().replace("FusedSGD", "FusedSGD[sm_100a flat]", 1)
+
+
+def make_optimizer(model: nn.Module, optimizer_type: str, optimizer_info: dict) -> Optimizer:
+    """Parameter grouping rules of reference utils/pipeline_ops.py:235-316, FusedSGD underneath."""
+    lr, mom = optimizer_info["lr"], optimizer_info["momentum"]
+    wd, nest = optimizer_info["weight_decay"], optimizer_info.get("nesterov", False)
+    named = list(model.named_parameters())
+    if optimizer_type == "sgd_trick":
+        is_light = lambda n: "bias" in n or "bn" in n                     # noqa: E731
+        groups = [{"params": [p for n, p in named if is_light(n)], "weight_decay": 0},
+                  {"params": [p for n, p in named if not is_light(n)]}]
+        return FusedSGD(groups, lr=lr, momentum=mom, weight_decay=wd, nesterov=nest, model=model)
+    if optimizer_type == "sgd_r3":
+        groups = [{"params": [p for n, p in named if n[-4:] == "bias"], "lr": 2 * lr},
+                  {"params": [p for n, p in named if n[-4:] != "bias"], "lr": lr, "weight_decay": wd}]
+        return FusedSGD(groups, momentum=mom, model=model)
+    if optimizer_type == "sgd_all":
+        return FusedSGD([p for _, p in named], lr=lr, weight_decay=wd, momentum=mom, model=model)
+    if optimizer_type == "adam":
+        return Adam(model.parameters(), lr=lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=wd)
+    if optimizer_type == "f3_trick":
+        backbone = [p for n, p in named if n.startswith("div") and not n.startswith("div_2")]
+        head = [p for n, p in named if not n.startswith("div")]
+        groups = [{"params": backbone, "lr": 0.1 * lr}, {"params": head, "lr": lr}]
+        return FusedSGD(groups, momentum=mom, weight_decay=wd, nesterov=nest, model=model)
+    raise NotImplementedError(optimizer_type)
+
+
+class CustomScheduler:
+    """LR schedules of reference utils/pipeline_ops.py:185-232, including its quirk: the coefficient is
+    evaluated once per param group and the warmup branches shrink `total_num` on every evaluation."""
+
+    def __init__(self, optimizer: Optimizer, total_num: int, scheduler_type: str, scheduler_info: dict):
+        self.lr_group = [g["lr"] for g in optimizer.param_groups]
+        self.total_num, self.type, self.info = total_num, scheduler_type, scheduler_info
+
+    def _coefficient(self, curr: int):
+        kind, decay = self.type, self.info["lr_decay"]
+        if kind == "poly":
+            return pow(1 - float(curr) / self.total_num, decay)
+        if kind in ("poly_warmup", "cosine_warmup"):
+            turn = self.info["warmup_epoch"]
+            if curr < turn:
+                return 1 / turn * (1 + curr)
+            curr -= turn - 1
+            self.total_num -= turn - 1
+            if kind == "poly_warmup":
+                return pow(1 - float(curr) / self.total_num, decay)
+            return (1 + np.cos(np.pi * curr / self.total_num)) / 2
+        if kind == "f3_sche":
+            return 1 - abs((curr + 1) / (self.total_num + 1) * 2 - 1)
+        raise NotImplementedError(kind)
+
+    def step(self, optimizer: Optimizer, curr_epoch: int):
+        for i, g in enumerate(optimizer.param_groups):
+            g["lr"] = self.lr_group[i] * self._coefficient(curr_epoch)
+
+    def __str__(self):
+        return f"Scheduler:\n\tType: {self.type}\n\tInfo: {self.info}\n"

@@ -1,0 +1,156 @@
+"""SyncBatchNorm seam: `convert_syncbn_model` + `SyncBatchNorm`, backed by csrc/syncbn.cu.
+
+Reference surface kept: `apex.parallel.convert_syncbn_model(model)` (reference train.py:16,180) — walks the
+module tree and swaps every BatchNorm for a synchronized one, returning the model.
+
+Decisions that differ from apex, on purpose:
+* Q2 — the swapped module SHARES the original `weight` / `bias` Parameter objects, so an optimizer built
+  before the conversion (reference train.py:157 vs :180) keeps training γ/β.
+* the module also exposes `fused_forward(x, pre_add=, residual=, relu=)`, used by the model plugins'
+  `bn_act` helper to fold the neighbouring add / ReLU into the same kernel.
+* one kernel launch per direction also when world_size == 1 (plain BN): the statistics "exchange" is then
+  the intra-GPU broadcast of the same packet mechanism.
+Inputs are processed as channels-last [N·H·W, C] matrices; other layouts are converted on entry.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _lib, comm
+
+_state: dict = {}
+TRACE: list | None = None   # bench.py: when a list, every forward call appends (n, c, h, w, has_pre, has_res, relu)
+
+
+def _dev_state(device: torch.device) -> dict:
+    st = _state.get(device.index)
+    if st is None:
+        nbytes = int(_lib.lib().sod_syncbn_workspace_bytes(1, 4096))
+        st = {"ws": torch.zeros(nbytes, dtype=torch.uint8, device=device), "seq": 0}
+        _state[device.index] = st
+    return st
+
+
+def _next_call(device: torch.device):
+    """(workspace, seq, comm_ref, stats_off): one global sequence over ALL BN launches of this process —
+    the packet tags must be unique across forward and backward calls that share slots."""
+    st = _dev_state(device)
+    st["seq"] = (st["seq"] + 1) & 0xFFFFFFFF or 1
+    seq = st["seq"]
+    arena = comm.small_arena()
+    if arena is None:
+        return st["ws"], seq, None, 0
+    return st["ws"], seq, arena.ref, arena.bn_slots[seq % len(arena.bn_slots)]
+
+
+def _as_rows(t: torch.Tensor) -> torch.Tensor:
+    """dense channels-last view of an NCHW-shaped tensor (copy only if it is not already laid out so)"""
+    if t.dim() != 4:
+        raise _lib.SodError(f"SyncBatchNorm expects 4-D input, got {t.dim()}-D")
+    return t if t.is_contiguous(memory_format=torch.channels_last) else t.contiguous(memory_format=torch.channels_last)
+
+
+class _SyncBNFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, pre_add, residual, weight, bias, running_mean, running_var, momentum, eps, relu, training):
+        x = _as_rows(x)
+        pre = _as_rows(pre_add).to(x.dtype) if pre_add is not None else None
+        res = _as_rows(residual).to(x.dtype) if residual is not None else None
+        n, c, h, w = x.shape
+        rows = n * h * w
+        if TRACE is not None:
+            TRACE.append((n, c, h, w, pre is not None, res is not None, bool(relu)))
+        y = torch.empty_like(x)  # preserves channels-last strides
+        dev = x.device
+        mean = torch.empty(c, dtype=torch.float32, device=dev)
+        invstd = torch.empty(c, dtype=torch.float32, device=dev)
+        ws, seq, cref, soff = _next_call(dev)
+        rc = _lib.lib().sod_syncbn_fwd(
+            x.data_ptr(), pre.data_ptr() if pre is not None else None, res.data_ptr() if res is not None else None,
+            y.data_ptr(), _lib.dtype_code(x.dtype), weight.data_ptr(), bias.data_ptr(),
+            running_mean.data_ptr() if running_mean is not None else None,
+            running_var.data_ptr() if running_var is not None else None,
+            mean.data_ptr(), invstd.data_ptr(), rows, c, float(momentum), float(eps), int(relu), int(training),
+            cref, soff, seq, ws.data_ptr(), ws.numel(), 0, _lib.stream_ptr())
+        _lib.check(rc, "sod_syncbn_fwd")
+        _lib.count_launch()
+        ctx.relu, ctx.has_pre, ctx.has_res = bool(relu), pre is not None, res is not None
+        ctx.save_for_backward(x, pre, y if relu else None, weight, mean, invstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, pre, y, weight, mean, invstd = ctx.saved_tensors
+        dz, dres, dgamma, dbeta = raw_backward(_as_rows(dy).to(x.dtype), x, pre, y, weight, mean, invstd, ctx.relu, ctx.has_res)
+        return (dz, dz if ctx.has_pre else None, dres, dgamma.to(weight.dtype), dbeta.to(weight.dtype),
+                None, None, None, None, None, None)
+
+
+def raw_backward(dy, x, pre, y, weight, mean, invstd, relu: bool, want_dres: bool):
+    """one `sod_syncbn_bwd` launch on channels-last tensors; returns (dz, dres|None, dgamma, dbeta)"""
+    n, c, h, w = x.shape
+    dz = torch.empty_like(x)
+    dres = torch.empty_like(x) if want_dres else None
+    dgamma = torch.empty(c, dtype=torch.float32, device=x.device)
+    dbeta = torch.empty(c, dtype=torch.float32, device=x.device)
+    ws, seq, cref, soff = _next_call(x.device)
+    rc = _lib.lib().sod_syncbn_bwd(
+        dy.data_ptr(), x.data_ptr(), pre.data_ptr() if pre is not None else None,
+        y.data_ptr() if (relu and y is not None) else None, dz.data_ptr(), dres.data_ptr() if dres is not None else None,
+        _lib.dtype_code(x.dtype), weight.data_ptr(), mean.data_ptr(), invstd.data_ptr(), dgamma.data_ptr(),
+        dbeta.data_ptr(), n * h * w, c, int(relu), cref, soff, seq, ws.data_ptr(), ws.numel(), 0, _lib.stream_ptr())
+    _lib.check(rc, "sod_syncbn_bwd")
+    _lib.count_launch()
+    return dz, dres, dgamma, dbeta
+
+
+class SyncBatchNorm(nn.BatchNorm2d):
+    """Drop-in for the module `convert_syncbn_model` installs (reference train.py:180)."""
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.fused_forward(x)
+
+    def fused_forward(self, x, pre_add=None, residual=None, relu=False):
+        if not x.is_cuda:
+            raise _lib.SodError("SyncBatchNorm: expected a CUDA tensor (the sm_100a kernel has no CPU fallback; "
+                                "keep nn.BatchNorm2d for CPU runs)")
+        if x.shape[1] != self.num_features:
+            raise ValueError(f"expected {self.num_features} channels, got {x.shape[1]}")
+        training = self.training or self.running_mean is None
+        momentum = 0.0
+        if training and self.track_running_stats:
+            if self.num_batches_tracked is not None:
+                self.num_batches_tracked.add_(1)
+            # momentum=None means cumulative average in torch; the reference never uses it
+            momentum = self.momentum if self.momentum is not None else 1.0 / float(self.num_batches_tracked)
+        rm = self.running_mean if self.track_running_stats else None
+        rv = self.running_var if self.track_running_stats else None
+        weight = self.weight if self.affine else torch.ones(self.num_features, device=x.device)
+        bias = self.bias if self.affine else torch.zeros(self.num_features, device=x.device)
+        return _SyncBNFn.apply(x, pre_add, residual, weight, bias, rm, rv, momentum, self.eps, relu, training)
+
+
+def convert_syncbn_model(module: nn.Module, process_group=None, channel_last: bool = True) -> nn.Module:
+    """Same call shape as apex's (reference train.py:180): returns the model with every `_BatchNorm` replaced
+    by `SyncBatchNorm`, parameters and buffers shared with the originals."""
+    if isinstance(module, nn.modules.batchnorm._BatchNorm) and not isinstance(module, SyncBatchNorm):
+        if not isinstance(module, nn.BatchNorm2d):
+            raise _lib.SodError(f"only BatchNorm2d is on the hot path, found {type(module).__name__}")
+        new = SyncBatchNorm(module.num_features, module.eps, module.momentum, module.affine, module.track_running_stats)
+        if module.affine:
+            new.weight, new.bias = module.weight, module.bias          # same Parameter objects (Q2)
+        new.running_mean, new.running_var = module.running_mean, module.running_var
+        new.num_batches_tracked = module.num_batches_tracked
+        new.train(module.training)
+        return new
+    for name, child in list(module.named_children()):
+        converted = convert_syncbn_model(child, process_group, channel_last)
+        if converted is not child:
+            if isinstance(module, nn.Sequential):
+                module[int(name)] = converted
+            else:
+                setattr(module, name, converted)
+    return module

@@ -1,0 +1,150 @@
+/* sod_b200.h — C ABI of libsod_b200.so: the B200 (sm_100a) data-parallel hot path of
+ * lartpang/Distributed-SOD-Project.
+ *
+ * The reference is pure Python and has NO FFI layer of its own: its hot path is reached
+ * through five Python call sites.  Each entry point below replaces the arithmetic behind one of them;
+ * the citation on each says which (paths relative to the reference repository).  A maintainer of the
+ * reference binds these with `ctypes` exactly as INTEGRATION.md shows.
+ *
+ * Conventions
+ *  - plain C: raw device pointers, element counts as int64_t, dtype enums, `void* stream` = cudaStream_t.
+ *  - the caller owns every buffer; the library allocates nothing and never synchronises the stream.
+ *  - return value: 0 ok; <0 contract error (sod_strerror); >0 a cudaError_t from the launch.
+ *  - re-entrant; callable from any host thread (PyTorch's autograd thread calls the *_bwd entries).
+ *  - collective entries (anything taking a sod_comm) must be called in the same order on every rank.
+ */
+#ifndef SOD_B200_H
+#define SOD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SOD_ABI_VERSION 1
+#define SOD_MAX_WORLD 8
+#define SOD_MAX_SEGMENTS 16
+#define SOD_COMM_MAX_BLOCKS 1024   /* flag rows per channel */
+#define SOD_COMM_CHANNELS 4        /* 0: grad reduce  1: syncbn fwd  2: syncbn bwd  3: plain all-reduce */
+
+typedef enum { SOD_F32 = 0, SOD_BF16 = 1, SOD_F16 = 2 } sod_dtype;
+
+enum {
+    SOD_OK = 0,
+    SOD_EINVAL = -1,       /* null pointer / negative size / bad enum */
+    SOD_EALIGN = -2,       /* pointer or offset not 16-byte aligned */
+    SOD_EWORKSPACE = -3,   /* workspace too small */
+    SOD_EUNSUPPORTED = -4, /* shape outside what the kernels cover (e.g. C % 8 != 0) */
+    SOD_ECOMM = -5         /* bad communicator (world > SOD_MAX_WORLD, missing peer pointer …) */
+};
+
+int sod_version(void);
+const char* sod_strerror(int code);
+/* sm count / compute capability of the current device; the hot path refuses anything but sm_100 */
+int sod_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------------
+ * (3) BCE-with-logits + CEL, forward AND backward in one kernel.
+ * Replaces: torch.nn.BCEWithLogitsLoss (train.py:203) + CEL.forward (loss/CEL.py:15-20) as summed by
+ *           get_total_loss (utils/pipeline_ops.py:37-42), and their autograd backward (train.py:302).
+ *   total = w_bce*BCE(reduction) + w_cel*CEL;  grad = grad_scale * d total / d logits
+ * scalars_out[8] (device, fp32): bce, cel, total, sum_p, sum_t, sum_pt, bce_sum(unreduced), n
+ * mode: 0 auto, 1 force the shared-memory-resident single-read path, 2 force the streaming two-pass path
+ * workspace: sod_loss_workspace_bytes() bytes, 16-byte aligned; contents need not be initialised.
+ * ------------------------------------------------------------------------------------------------ */
+size_t sod_loss_workspace_bytes(void);
+int sod_loss_bce_cel_fwd_bwd(const void* logits, int logits_dtype, const void* mask, int mask_dtype,
+                             void* grad_logits, int grad_dtype, float* scalars_out, int64_t n,
+                             int reduction_sum, float w_bce, float w_cel, float grad_scale, float eps,
+                             int mode, void* workspace, size_t workspace_bytes, void* stream);
+/* grad *= *scale_dev (device scalar): only for the case where the loss is not the root of backward */
+int sod_scale_by_device_scalar(void* grad, int dtype, int64_t n, const float* scale_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Symmetric-memory communicator (one process per GPU; all ranks on one NVSwitch domain).
+ * Built by the host from torch.distributed._symmetric_memory (buffer_ptrs / multicast_ptr): `peer[r]`
+ * is rank r's arena as mapped into THIS process, `mc` the multicast (NVLS) mapping of the same arena
+ * or 0.  Replaces the NCCL communicator of dist.init_process_group (train.py:73-77) for the hot path.
+ * The first sod_comm_flag_bytes() bytes of every arena are the signal area and must be zeroed once
+ * (before the first collective, followed by a process-group barrier).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+    int32_t rank;
+    int32_t world;
+    uint64_t peer[SOD_MAX_WORLD];
+    uint64_t mc;
+    uint64_t arena_bytes;
+    uint32_t* error_flag;   /* device word in local memory; set non-zero on a barrier timeout */
+    uint64_t timeout_cycles;/* bounded spin; 0 = default (~20 s) */
+} sod_comm;
+size_t sod_comm_flag_bytes(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * (1) gradient all-reduce ⊕ unscale ⊕ SGD-momentum.
+ * Replaces: apex DDP(delay_allreduce=True) flat all-reduce + ×1/W (train.py:185), amp unscale
+ *           (train.py:299), torch.optim.SGD.step as configured by make_optimizer
+ *           (utils/pipeline_ops.py:295-313; train.py:303), and optimizer.zero_grad (train.py:297).
+ * Flat fp32 buffers of n elements (n % 4 == 0), laid out group-major; `segs` (host array) gives each
+ * contiguous range its lr / weight_decay / momentum; SOD_SEG_FROZEN ranges receive the averaged
+ * gradient but p and v are left alone (the reference leaves `div_2.*` out of every param group).
+ *   g = (Σ_ranks grad) * inv_scale / world + wd*p ;  v = mu*v + g ;  p -= lr*v
+ * world==1 (comm NULL): purely local.  world>1: grad and param live in the arena at grad_off/param_off;
+ * rank r reduces shard r (NVLS multimem.ld_reduce when comm->mc != 0 and algo allows, else peer loads
+ * in rank order), updates its shard of p and v, and writes the new p to every rank (multimem.st / peer
+ * stores).  `mom` is the local momentum buffer, full length n (only shard r is used when world>1).
+ * found_inf (device, may be NULL): when non-NULL and *found_inf != 0 the whole step is skipped.
+ * flags: SOD_SGD_ZERO_GRAD zeroes the local gradient buffer on the way out.
+ * ------------------------------------------------------------------------------------------------ */
+enum { SOD_SEG_FROZEN = 1 };
+typedef struct {
+    int64_t begin, end;        /* element range, multiples of 4 */
+    float lr, weight_decay, momentum;
+    int32_t flags;
+} sod_sgd_segment;
+enum { SOD_SGD_ZERO_GRAD = 1, SOD_ALGO_NO_MULTIMEM = 2 };
+
+int sod_sgd_momentum(float* param, float* mom, float* grad, int64_t n, const sod_sgd_segment* segs,
+                     int nseg, float inv_scale, const uint32_t* found_inf, int flags, void* stream);
+int sod_allreduce_sgd(const sod_comm* comm, uint64_t grad_off, uint64_t param_off, float* mom, int64_t n,
+                      const sod_sgd_segment* segs, int nseg, float inv_scale, const uint32_t* found_inf,
+                      uint32_t seq, int flags, void* stream);
+/* *found_inf |= any(!isfinite(grad)) — the amp overflow check (train.py:299), one read of grad */
+int sod_grad_nonfinite(const float* grad, int64_t n, uint32_t* found_inf, void* stream);
+
+/* plain in-place SUM all-reduce of fp32 data at arena offset `off` (BASELINE config 5 sweep; also the
+ * scalar loss mean of utils/tensor_ops.py:60-64 with scale = 1/W).  algo: 0 auto, 1 one-shot, 2 two-shot */
+int sod_allreduce_f32(const sod_comm* comm, uint64_t off, int64_t n, float scale, int algo, uint32_t seq,
+                      int flags, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (2) SyncBatchNorm, statistics exchange fused with normalize/affine (+ optional pre-add, residual, ReLU).
+ * Replaces: apex convert_syncbn_model/SyncBatchNorm forward+backward (train.py:180) — local Welford +
+ *           2 all_gathers + elementwise forward; reduce + 2 all_reduces + elementwise backward.
+ * Data layout: channels-last matrices [M = N*H*W rows, C channels] (x_dtype ∈ bf16/f16/f32; C % 8 == 0
+ * for 16-bit, C % 4 == 0 for f32), fp32 gamma/beta/running stats/saved stats.
+ *   z = x (+ pre_add);  mean/var over M*world rows;  y = relu?((z-mean)*invstd*gamma + beta (+ residual))
+ * training=0: uses running stats, no exchange.  comm may be NULL (world 1).
+ * stats_off: arena offset of the exchange slots (sod_syncbn_exchange_bytes(C) per layer call; the host
+ * rotates ≥2 slots); seq: per-channel sequence number, same on all ranks, strictly increasing.
+ * ------------------------------------------------------------------------------------------------ */
+size_t sod_syncbn_workspace_bytes(int64_t rows, int channels);
+size_t sod_syncbn_exchange_bytes(int channels);
+int sod_syncbn_fwd(const void* x, const void* pre_add, const void* residual, void* y, int dtype,
+                   const float* gamma, const float* beta, float* running_mean, float* running_var,
+                   float* save_mean, float* save_invstd, int64_t rows, int channels, float momentum,
+                   float eps, int relu, int training, const sod_comm* comm, uint64_t stats_off, uint32_t seq,
+                   void* workspace, size_t workspace_bytes, int flags, void* stream);
+/* dz = d/d(x) = d/d(pre_add); dres = relu-masked dy (written only if non-NULL; may alias nothing);
+ * dgamma/dbeta: LOCAL sums (the gradient all-reduce averages them with every other parameter). */
+int sod_syncbn_bwd(const void* dy, const void* x, const void* pre_add, const void* y, void* dz, void* dres,
+                   int dtype, const float* gamma, const float* save_mean, const float* save_invstd,
+                   float* dgamma, float* dbeta, int64_t rows, int channels, int relu, const sod_comm* comm,
+                   uint64_t stats_off, uint32_t seq, void* workspace, size_t workspace_bytes, int flags,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOD_B200_H */

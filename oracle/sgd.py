@@ -85,7 +85,7 @@ class SchedulerState:
     def coefficient(self, curr: int) -> float:
         k = self.kind
         if k == "poly":
-            return math.pow(1 - float(curr) / self.total_num, self.lr_decay)
+            return pow(1 - float(curr) / self.total_num, self.lr_decay)  # builtin pow: complex when base<0, like the reference
         if k in ("poly_warmup", "cosine_warmup"):
             turn = self.warmup_epoch
             if curr < turn:
@@ -93,7 +93,7 @@ class SchedulerState:
             curr -= turn - 1
             self.total_num -= turn - 1       # reference mutates its own state here
             if k == "poly_warmup":
-                return math.pow(1 - float(curr) / self.total_num, self.lr_decay)
+                return pow(1 - float(curr) / self.total_num, self.lr_decay)  # builtin pow: complex when base<0, like the reference
             return float((1 + np.cos(np.pi * curr / self.total_num)) / 2)
         if k == "f3_sche":
             return 1 - abs((curr + 1) / (self.total_num + 1) * 2 - 1)

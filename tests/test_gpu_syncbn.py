@@ -1,0 +1,123 @@
+"""Parity of the SyncBN kernels (world 1 here; world 2 in test_gpu_multi.py) with the fp64 oracle and with
+torch's own batch_norm autograd."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from oracle import syncbn as obn
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [  # N, C, H, W  — the channel counts of the TestModel's 84 BN layers, plus ragged row counts
+    (2, 32, 5, 7), (16, 64, 80, 80), (4, 64, 33, 31), (2, 128, 9, 9), (16, 256, 20, 20), (3, 512, 7, 5),
+    (16, 1024, 20, 20), (2, 2048, 2, 2), (16, 2048, 10, 10), (1, 64, 1, 1), (16, 32, 160, 160),
+]
+
+
+def _mk(shape, dtype, seed, scale=1.0, shift=0.0):
+    g = torch.Generator().manual_seed(seed)
+    t = (torch.randn(shape, generator=g) * scale + shift).to(dtype)
+    return t.cuda().contiguous(memory_format=torch.channels_last)
+
+
+def _bn(c):
+    from distributed_sod_project_b200.syncbn import SyncBatchNorm
+    bn = SyncBatchNorm(c).cuda()
+    with torch.no_grad():
+        bn.weight.copy_(torch.linspace(0.5, 1.5, c)); bn.bias.copy_(torch.linspace(-0.3, 0.3, c))
+    return bn
+
+
+def _tol(dtype):
+    return dict(rtol=2e-2, atol=2e-2) if dtype != torch.float32 else dict(rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("variant", ["plain", "relu", "pre_relu", "res_relu", "all"])
+def test_forward_backward_vs_oracle(shape, dtype, variant):
+    n, c, h, w = shape
+    x = _mk(shape, dtype, 1, 1.5, 0.3).requires_grad_(True)
+    pre = _mk(shape, dtype, 2).requires_grad_(True) if variant in ("pre_relu", "all") else None
+    res = _mk(shape, dtype, 3).requires_grad_(True) if variant in ("res_relu", "all") else None
+    relu = variant != "plain"
+    bn = _bn(c)
+    rm0, rv0 = bn.running_mean.clone(), bn.running_var.clone()
+    y = bn.fused_forward(x, pre_add=pre, residual=res, relu=relu)
+    dy = _mk(shape, dtype, 4)
+    y.backward(dy)
+    torch.cuda.synchronize()
+
+    f64 = lambda t: None if t is None else t.detach().float().cpu().numpy().astype(np.float64)  # noqa: E731
+    ref = obn.syncbn_forward([f64(x)], f64(bn.weight), f64(bn.bias), f64(rm0), f64(rv0),
+                             pre_adds=None if pre is None else [f64(pre)],
+                             residuals=None if res is None else [f64(res)], relu=relu)
+    tol = _tol(dtype)
+    np.testing.assert_allclose(f64(y), ref["ys"][0], **tol)
+    if n * h * w > 1:
+        np.testing.assert_allclose(f64(bn.running_mean), ref["running_mean"], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(f64(bn.running_var), ref["running_var"], rtol=1e-3, atol=1e-5)
+    # backward: the oracle masks with ITS y; use the kernel's y so a value sitting exactly on 0 cannot flip
+    rb = obn.syncbn_backward([f64(dy)], ref["zs"], [f64(y)], ref["mean"], ref["invstd"], f64(bn.weight), relu=relu)
+    gscale = max(np.abs(rb["dzs"][0]).max(), 1e-6)
+    btol = 3e-2 if dtype != torch.float32 else 2e-4
+    assert np.abs(f64(x.grad) - rb["dzs"][0]).max() / gscale < btol
+    if pre is not None:
+        assert torch.equal(pre.grad, x.grad)
+    if res is not None:
+        assert np.abs(f64(res.grad) - rb["dresiduals"][0]).max() <= 1e-6 + 1e-2 * (dtype != torch.float32)
+    rows = n * h * w
+    np.testing.assert_allclose(f64(bn.weight.grad), rb["dgammas"][0], rtol=btol, atol=btol * max(1.0, rows ** 0.5))
+    np.testing.assert_allclose(f64(bn.bias.grad), rb["dbetas"][0], rtol=btol, atol=btol * max(1.0, rows ** 0.5))
+    assert int(bn.num_batches_tracked) == 1
+    assert y.is_contiguous(memory_format=torch.channels_last) and y.dtype == dtype
+
+
+@pytest.mark.parametrize("shape", [(16, 64, 80, 80), (2, 2048, 2, 2), (5, 256, 13, 11)])
+def test_matches_torch_batch_norm_fp32(shape):
+    """independent cross-check: torch's BatchNorm2d (train mode) + ReLU with autograd"""
+    n, c, h, w = shape
+    x1 = _mk(shape, torch.float32, 7, 2.0, -0.5).requires_grad_(True)
+    x2 = x1.detach().clone().requires_grad_(True)
+    bn = _bn(c)
+    tbn = nn.BatchNorm2d(c).cuda()
+    tbn.load_state_dict(bn.state_dict())
+    dy = _mk(shape, torch.float32, 8)
+    bn.fused_forward(x1, relu=True).backward(dy)
+    F.relu(tbn(x2)).backward(dy)
+    assert torch.allclose(x1.grad, x2.grad, rtol=1e-3, atol=1e-4)
+    assert torch.allclose(bn.weight.grad, tbn.weight.grad, rtol=1e-3, atol=1e-3)
+    assert torch.allclose(bn.running_var, tbn.running_var, rtol=1e-4, atol=1e-6)
+
+
+def test_eval_mode_and_nchw_input():
+    bn = _bn(64)
+    with torch.no_grad():
+        bn.running_mean.normal_(); bn.running_var.uniform_(0.5, 2.0)
+    bn.eval()
+    x = torch.randn(3, 64, 11, 9, device="cuda")                       # plain NCHW: converted on entry
+    y = bn(x)
+    ref = F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bias=bn.bias, training=False, eps=bn.eps)
+    assert torch.allclose(y, ref, rtol=1e-5, atol=1e-5)
+    assert int(bn.num_batches_tracked) == 0
+
+
+def test_convert_shares_parameters_and_rejects_cpu():
+    from distributed_sod_project_b200 import _lib
+    from distributed_sod_project_b200.syncbn import SyncBatchNorm, convert_syncbn_model
+    net = nn.Sequential(nn.Conv2d(3, 8, 3), nn.BatchNorm2d(8), nn.ReLU(), nn.Sequential(nn.BatchNorm2d(8)))
+    w = net[1].weight
+    out = convert_syncbn_model(net)
+    assert out is net and isinstance(net[1], SyncBatchNorm) and isinstance(net[3][0], SyncBatchNorm)
+    assert net[1].weight is w                                            # Q2: optimizer built earlier keeps γ/β
+    with pytest.raises(_lib.SodError):
+        net[1](torch.zeros(1, 8, 2, 2))
+
+
+def test_repeated_calls_are_deterministic():
+    bn = _bn(256)
+    x = _mk((16, 256, 20, 20), torch.bfloat16, 11)
+    ys = [bn.fused_forward(x, relu=True).clone() for _ in range(5)]
+    assert all(torch.equal(ys[0], y) for y in ys[1:])

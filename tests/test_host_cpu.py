@@ -1,0 +1,148 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol of include/sod_b200.h, host-side layout
+logic (flat parameter storage, optimizer grouping, scheduler), and the model plugins' contract."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from distributed_sod_project_b200 import _lib, build
+    build.build()
+    header = open(os.path.join(ROOT, "include", "sod_b200.h")).read()
+    declared = set(re.findall(r"\b(sod_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no prototypes found"
+    h = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(h, name), f"{name} declared in include/sod_b200.h but not exported"
+    assert declared == set(_lib.EXPORTS)
+    lib = _lib.lib()
+    assert lib.sod_version() == 1
+    assert lib.sod_comm_flag_bytes() == 4 * 1024 * 8 * 4
+    assert lib.sod_syncbn_exchange_bytes(64) == 8 * 2 * 64 * 8
+    assert b"workspace" in lib.sod_strerror(-3)
+    # struct layout agrees with the header (sizes are part of the ABI)
+    assert ctypes.sizeof(_lib.sod_sgd_segment) == 32 and ctypes.sizeof(_lib.sod_comm) == 8 + 64 + 8 + 8 + 8 + 8
+
+
+def test_no_cpu_fallback_in_product_path():
+    from distributed_sod_project_b200 import _lib
+    from distributed_sod_project_b200.loss import CEL
+    from distributed_sod_project_b200.syncbn import SyncBatchNorm
+    with pytest.raises(_lib.SodError):
+        CEL()(torch.zeros(4), torch.zeros(4))
+    with pytest.raises(_lib.SodError):
+        SyncBatchNorm(8)(torch.zeros(1, 8, 2, 2))
+    # and nothing under the package imports the oracle
+    pkg = os.path.join(ROOT, "distributed_sod_project_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+
+
+def test_model_plugin_contract():
+    from distributed_sod_project_b200 import network
+    from distributed_sod_project_b200.utils import init_seed
+    init_seed(0)
+    m = network.res50()
+    names = [n for n, _ in m.named_parameters()]
+    assert len(names) == 319 and sum(p.numel() for p in m.parameters()) == 24_906_305
+    assert names[0] == "div_2.0.weight" and names[-1] == "classifier.bias"
+    assert sum(isinstance(x, nn.BatchNorm2d) for x in m.modules()) == 84
+    backbone = [n for n in names if n.startswith("div") and not n.startswith("div_2")]
+    head = [n for n in names if not n.startswith("div")]
+    assert (len(backbone), len(head), len(names) - len(backbone) - len(head)) == (156, 160, 3)
+    m.eval()
+    with torch.no_grad():
+        assert m(torch.zeros(1, 3, 64, 64)).shape == (1, 1, 64, 64)
+    assert network.cp_res50.recompute and not network.res50.recompute
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference only exists in the build container")
+def test_model_plugin_is_bit_identical_to_reference():
+    import subprocess, sys
+    code = r'''
+import sys, types, torch, hashlib
+sys.path.insert(0, "/root/reference"); sys.path.insert(0, %r)
+m = types.ModuleType("torchvision.models.utils"); m.load_state_dict_from_url = lambda *a, **k: {}
+sys.modules["torchvision.models.utils"] = m
+for n in ("openpyxl", "thop"):
+    mm = types.ModuleType(n); mm.load_workbook = mm.Workbook = mm.profile = None; sys.modules[n] = mm
+import torch.utils.model_zoo as mz; mz.load_url = lambda *a, **k: {}
+from utils.misc import init_seed
+import network as ref
+from distributed_sod_project_b200 import network as mine
+init_seed(0); a = ref.res50(); init_seed(0); b = mine.res50()
+assert list(a.state_dict()) == list(b.state_dict())
+assert all(torch.equal(x, y) for x, y in zip(a.state_dict().values(), b.state_dict().values()))
+x = torch.randn(2, 3, 64, 64)
+assert torch.equal(a(x), b(x))
+print("IDENTICAL")
+''' % ROOT
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert "IDENTICAL" in out.stdout, out.stderr[-2000:]
+
+
+def test_flat_params_layout_cpu():
+    from distributed_sod_project_b200 import network
+    from distributed_sod_project_b200.optim import FusedSGD, make_optimizer
+    m = network.res50().to(memory_format=torch.channels_last)
+    w_before = m.div_4[1][0].conv2.weight.detach().clone()
+    opt = make_optimizer(m, "f3_trick", dict(lr=0.05, momentum=0.9, weight_decay=5e-4, nesterov=False))
+    assert isinstance(opt, FusedSGD)
+    f = opt.flat
+    (b0, e0), (b1, e1), (b2, e2) = f.ranges
+    assert b0 == 0 and e0 == b1 and e1 == b2 and e2 == f.numel and f.numel % 64 == 0
+    assert [g["lr"] for g in opt.param_groups] == pytest.approx([0.005, 0.05])
+    # views, not copies; memory format preserved; values preserved
+    w = m.div_4[1][0].conv2.weight
+    assert w.data_ptr() >= f.param.data_ptr() and w.data_ptr() < f.param.data_ptr() + 4 * f.numel
+    assert w.is_contiguous(memory_format=torch.channels_last) and torch.equal(w.detach(), w_before)
+    assert w.grad is not None and w.grad.stride() == w.stride()
+    frozen = dict(m.named_parameters())["div_2.0.weight"]
+    assert frozen.data_ptr() >= f.param.data_ptr() + 4 * b2
+    segs, n = opt._segments()
+    assert n == 3 and segs[2].flags == 1 and abs(segs[0].lr - 0.005) < 1e-9 and abs(segs[1].weight_decay - 5e-4) < 1e-9
+    # autograd accumulates INTO the flat buffer
+    m.train()
+    m(torch.randn(2, 3, 64, 64)).sum().backward()
+    assert float(f.grad.abs().sum()) > 0
+    opt.zero_grad()
+    assert float(f.grad.abs().sum()) == 0
+    from distributed_sod_project_b200 import _lib
+    with pytest.raises(_lib.SodError):
+        opt.step()          # CPU parameters: the fused step refuses instead of falling back
+
+
+def test_scheduler_matches_reference_table(golden):
+    from distributed_sod_project_b200.optim import CustomScheduler
+    g = golden("sgd_kat.npz")
+
+    class _Opt:
+        param_groups = [{"lr": 0.005}, {"lr": 0.05}]
+    for kind in ("poly", "poly_warmup", "cosine_warmup", "f3_sche"):
+        opt = _Opt(); opt.param_groups = [{"lr": 0.005}, {"lr": 0.05}]
+        sch = CustomScheduler(opt, total_num=30, scheduler_type=kind, scheduler_info=dict(lr_decay=0.9, warmup_epoch=3))
+        for e, row in enumerate(g[f"sched/{kind}"]):
+            sch.step(opt, curr_epoch=e)
+            got = [gr["lr"] for gr in opt.param_groups]
+            if any(isinstance(v, complex) for v in got) or np.isnan(row).any():
+                break
+            np.testing.assert_allclose(got, row, rtol=1e-12)
+
+
+def test_exp_name_and_paths():
+    import config
+    from distributed_sod_project_b200.utils import construct_exp_name, construct_path_dict
+    name = construct_exp_name(config.user_config)
+    assert name.startswith(config.user_config["model"] + "_SIZE320_BS")
+    paths = construct_path_dict(config.user_config["proj_root"], name, config.user_config["xlsx_name"])
+    assert paths["final_full_net"].endswith("pth/checkpoint_final.pth.tar")
