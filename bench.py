@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "torch"])
     ap.add_argument("--model", default="res50", choices=["res50", "cp_res50"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -106,7 +106,7 @@ def cpu_reference(model_name: str, batch: int, steps: int, warmup: int):
     from oracle.step import OracleTrainer
     from distributed_sod_project_b200 import network
     from distributed_sod_project_b200.synthetic import synth_batch
-    cores = os.cpu_count() or 1
+    cores = pick_threads(getattr(network, model_name))
     torch.set_num_threads(cores)
     tr = OracleTrainer(getattr(network, model_name), world_size=1, seed=0)
     batches = [synth_batch(1234 + i, batch, SIZE) for i in range(2)]
@@ -120,6 +120,36 @@ def cpu_reference(model_name: str, batch: int, steps: int, warmup: int):
             "sample": f"{steps} steps of bs={batch} at {SIZE}x{SIZE} fp32 ({model_name}, oracle/step.py restatement of "
                       f"reference train.py:284-310 on my network plugin, {cores} torch threads, world 1)",
             "ms_per_step": dt * 1e3}
+
+
+def pick_threads(factory) -> int:
+    """torch intra-op thread count that is actually fastest on this host: the box may expose far more logical CPUs
+    than the container is allowed to use (128 visible on the GPU pool; over-subscription made a step >100 s)."""
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    try:   # cgroup v2 quota
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            avail = max(1, min(avail, int(int(q) / int(per) + 0.5)))
+    except (OSError, ValueError):
+        pass
+    cands = sorted({c for c in (4, 8, 16, 32, 64) if c <= avail} | {min(avail, 64)})
+    model = factory().train()
+    x = torch.randn(2, 3, 160, 160)
+    best, best_t = cands[0], float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        model(x).sum().backward()
+        t0 = time.perf_counter()
+        model(x).sum().backward()
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = c, dt
+        if dt > 4 * best_t:
+            break
+    return best
 
 
 def run_reference_arm(args):
@@ -175,6 +205,46 @@ def bn_roofline(trace, dtype, iters=5):
     return total_bytes / (total_ms * 1e-3) / 1e9, total_ms / (iters * len(layers)), total_bytes / (iters * len(layers))
 
 
+class TorchEagerTrainer:
+    """Same iteration with stock PyTorch on the GPU (nn.BatchNorm2d, torch losses, torch.optim.SGD(fused=True),
+    bf16 autocast, channels-last): NOT the reference arm — the "what you get without this repo's kernels" line."""
+
+    def __init__(self, model_name, dtype):
+        from oracle.step import OracleCEL, f3_trick_groups
+        from distributed_sod_project_b200 import network
+        from distributed_sod_project_b200.utils import init_seed
+        init_seed(0)
+        self.model = getattr(network, model_name)().cuda().to(memory_format=torch.channels_last)
+        self.opt = torch.optim.SGD(f3_trick_groups(self.model, 0.05), momentum=0.9, weight_decay=5e-4, fused=True)
+        self.loss_funcs = [torch.nn.BCEWithLogitsLoss(), OracleCEL()]
+        self.dtype = dtype
+        self.world = 1
+        self.model.train()
+        self._pinned = torch.zeros(1).pin_memory()
+
+    def forward_backward_update(self, x, m):
+        x = x.contiguous(memory_format=torch.channels_last)
+        with torch.autocast("cuda", dtype=self.dtype, enabled=self.dtype != torch.float32):
+            preds = self.model(x)
+        loss = sum(f(preds.float(), m) for f in self.loss_funcs)
+        self.opt.zero_grad(set_to_none=True)
+        loss.backward()
+        self.opt.step()
+        return loss.detach(), None, preds
+
+    def step_from_host(self, xh, mh):
+        loss, _, _ = self.forward_backward_update(xh.cuda(non_blocking=True), mh.cuda(non_blocking=True))
+        self._pinned.copy_(loss.reshape(1), non_blocking=True)
+
+    def last_loss(self):
+        torch.cuda.synchronize()
+        return float(self._pinned[0])
+
+    @property
+    def module(self):
+        return self.model
+
+
 def run_b200_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -189,7 +259,12 @@ def run_b200_arm(args):
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     args.warmup = max(3, args.warmup)          # timing rule: at least 3 warm-up iterations
     torch.backends.cudnn.benchmark = True
-    tr = Trainer(model_name=args.model, dtype=dtype, channels_last=True, report_items=False)
+    log('building trainer')
+    if args.impl == "torch":
+        tr = TorchEagerTrainer(args.model, dtype)
+    else:
+        tr = Trainer(model_name=args.model, dtype=dtype, channels_last=True, report_items=False)
+    log('trainer built')
     nb = 4
     host = [synth_batch(1234 + rank + 100 * i, BS, SIZE) for i in range(nb)]
     host = [(x.pin_memory(), m.pin_memory()) for x, m in host]
@@ -219,12 +294,24 @@ def run_b200_arm(args):
     syncbn.TRACE = []
     for i in range(args.warmup):
         tr.forward_backward_update(*dev[i % nb])
+        torch.cuda.synchronize(); log(f'warmup {i} done')
         if i == 0:
             trace, syncbn.TRACE = syncbn.TRACE, None
     l0 = _lib.launches
+    if os.environ.get("SOD_BENCH_PROFILE"):
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            for i in range(2):
+                tr.forward_backward_update(*dev[i % nb])
+            torch.cuda.synchronize()
+        with open(os.environ["SOD_BENCH_PROFILE"], "w") as f:
+            f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90))
+    rid = torch.cuda.nvtx.range_start("timed")      # start/end range: process-wide (backward runs on autograd's thread)
     with ClockSampler(local) as clk:
         ms = timed(lambda i: tr.forward_backward_update(*dev[i % nb]), args.steps)
+    torch.cuda.nvtx.range_end(rid)
     launches = _lib.launches - l0
+    log(f'timed region done: {ms / args.steps:.2f} ms/step')
     value = world * BS * args.steps / (ms * 1e-3)
 
     # -- end-to-end arm: pinned host batch in, loss out, every step ------------------------------------
@@ -233,6 +320,13 @@ def run_b200_arm(args):
     tr.last_loss()
     ms_e2e = timed(lambda i: (tr.step_from_host(*host[i % nb]), tr.last_loss() if i == args.steps - 1 else None), args.steps)
     e2e = world * BS * args.steps / (ms_e2e * 1e-3)
+    log(f'e2e done: {ms_e2e / args.steps:.2f} ms/step')
+    if args.impl == "torch":
+        if rank == 0:
+            print(json.dumps({"impl": "torch-eager", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+                              "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "dtype": args.dtype,
+                              "e2e": {"value": e2e, "unit": UNIT}, "clocks": clk.summary()}), flush=True)
+        return
     if tr.world > 1 and hasattr(tr.model, "arena") and tr.model.arena is not None:
         tr.model.arena.check_error()
 
@@ -245,6 +339,7 @@ def run_b200_arm(args):
     from distributed_sod_project_b200.syncbn import SyncBatchNorm
     n_bn = sum(isinstance(mod, SyncBatchNorm) for mod in tr.module.modules())
     bw, avg_ms, avg_bytes = bn_roofline(trace[:n_bn], dtype)   # cp_res50 traces its recompute forwards too
+    log(f'roofline replay done: {bw:.0f} GB/s')
     roof = {"bound": "hbm", "kernel": "syncbn_bwd_kernel (84 launches/iteration, replayed alone on the model's layer shapes, "
                                       "L2 flushed between launches)",
             "achieved": bw, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": bw / pk["hbm_gbs"], "peak_kind": pk_kind,
@@ -315,8 +410,18 @@ def run_sweep(args):
     dist.barrier(); dist.destroy_process_group()
 
 
+def log(msg):
+    if os.environ.get("SOD_BENCH_VERBOSE"):
+        print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 def main():
     args = parse()
+    if args.impl == "torch":
+        return run_b200_arm(args)
+    if os.environ.get("SOD_BENCH_VERBOSE"):
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ.get("SOD_BENCH_WATCHDOG", "120")), repeat=True, file=sys.stderr)
     if args.sweep:
         return run_sweep(args)
     if args.impl == "reference":

@@ -61,8 +61,12 @@ def test_forward_backward_vs_oracle(shape, dtype, variant):
         np.testing.assert_allclose(f64(bn.running_var), ref["running_var"], rtol=1e-3, atol=1e-5)
     # backward: the oracle masks with ITS y; use the kernel's y so a value sitting exactly on 0 cannot flip
     rb = obn.syncbn_backward([f64(dy)], ref["zs"], [f64(y)], ref["mean"], ref["invstd"], f64(bn.weight), relu=relu)
-    gscale = max(np.abs(rb["dzs"][0]).max(), 1e-6)
     btol = 3e-2 if dtype != torch.float32 else 2e-4
+    if n * h * w == 1:
+        # degenerate: one value per channel ⇒ var = 0, invstd = 1/sqrt(eps) ≈ 316 amplifies rounding; dz is 0 exactly
+        assert np.abs(f64(x.grad)).max() < 1e-3
+        return
+    gscale = max(np.abs(rb["dzs"][0]).max(), 1e-6)
     assert np.abs(f64(x.grad) - rb["dzs"][0]).max() / gscale < btol
     if pre is not None:
         assert torch.equal(pre.grad, x.grad)

@@ -192,9 +192,13 @@ def main():
     torch.set_num_threads(8)
     loss_kats()
     sgd_kats()
+    # 64x64 / bs 2 leaves 8 samples under the deepest BN: a deliberately ill-conditioned edge case (kept for the
+    # first-iteration checks); 128x128 / bs 4 is the well-conditioned small configuration
     step_vectors("res50", 1, 2, 64, 6, "res50_w1_s64", keep_logits=(0, 5))
     step_vectors("cp_res50", 1, 2, 64, 3, "cp_res50_w1_s64", keep_logits=(0,))
     step_vectors("res50", 2, 2, 64, 4, "res50_w2_s64", keep_logits=(0, 3))
+    step_vectors("res50", 1, 4, 128, 4, "res50_w1_s128", keep_logits=(0,))
+    step_vectors("res50", 2, 4, 128, 4, "res50_w2_s128", keep_logits=(0,))
     step_vectors("res50", 1, 4, 320, 3, "res50_w1_s320", keep_logits=())   # BASELINE config 1 shape
 
 
