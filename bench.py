@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=4)
     ap.add_argument("--sweep", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay of the iteration")
     return ap.parse_args()
 
 
@@ -174,7 +175,9 @@ def run_reference_arm(args):
 def bn_roofline(trace, dtype, iters=5):
     """replay every SyncBN backward launch of one iteration (same shapes, same fusion flags), alone, timed with
     CUDA events on the launching stream; L2 is flushed between launches by a 256 MB write."""
+    from distributed_sod_project_b200 import syncbn as _sbn
     from distributed_sod_project_b200.syncbn import raw_backward
+    _sbn.FORCE_LOCAL = True
     esz = 2 if dtype != torch.float32 else 4
     layers = []
     for (n, c, h, w, has_pre, has_res, relu) in trace:
@@ -185,10 +188,12 @@ def bn_roofline(trace, dtype, iters=5):
         weight = torch.ones(c, device="cuda")
         mean = torch.zeros(c, device="cuda"); invstd = torch.ones(c, device="cuda")
         elems = n * c * h * w
-        # algorithmic bytes (10 B/elem for plain bf16 = two reads of dy,x + one write of dx), extended
-        # for the fused operands: each extra read operand is read in both passes, each extra output written once
+        # algorithmic bytes = compulsory traffic: every input operand read ONCE, every output written once
+        # (SURVEY §8d's 10 B/elem assumed two passes over dy,x; the kernel keeps its strip in shared memory between
+        # the reduction and the elementwise phase, so the honest denominator is the single-pass figure: 6 B/elem
+        # for plain bf16 backward, +2 B/elem per fused operand)
         reads = 2 + (1 if has_pre else 0) + (1 if relu else 0)
-        byts = (2 * reads + 1 + (1 if has_res else 0)) * esz * elems
+        byts = (reads + 1 + (1 if has_res else 0)) * esz * elems
         layers.append(((dy, x, pre, y, weight, mean, invstd, relu, has_res), byts))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     total_ms, total_bytes = 0.0, 0
@@ -202,6 +207,7 @@ def bn_roofline(trace, dtype, iters=5):
             e.synchronize()
             if it > 0:
                 total_ms += s.elapsed_time(e); total_bytes += byts
+    _sbn.FORCE_LOCAL = False
     return total_bytes / (total_ms * 1e-3) / 1e9, total_ms / (iters * len(layers)), total_bytes / (iters * len(layers))
 
 
@@ -263,7 +269,7 @@ def run_b200_arm(args):
     if args.impl == "torch":
         tr = TorchEagerTrainer(args.model, dtype)
     else:
-        tr = Trainer(model_name=args.model, dtype=dtype, channels_last=True, report_items=False)
+        tr = Trainer(model_name=args.model, dtype=dtype, channels_last=True, report_items=False, use_graph=not args.no_graph)
     log('trainer built')
     nb = 4
     host = [synth_batch(1234 + rank + 100 * i, BS, SIZE) for i in range(nb)]

@@ -26,7 +26,7 @@ class SodError(RuntimeError):
 class sod_comm(C.Structure):
     _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("peer", C.c_uint64 * SOD_MAX_WORLD),
                 ("mc", C.c_uint64), ("arena_bytes", C.c_uint64), ("error_flag", C.c_void_p),
-                ("timeout_cycles", C.c_uint64)]
+                ("timeout_cycles", C.c_uint64), ("block_seq", C.c_void_p)]
 
 
 class sod_sgd_segment(C.Structure):
@@ -47,20 +47,19 @@ _PROTOTYPES = {
     "sod_sgd_momentum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(sod_sgd_segment), C.c_int,
                                    C.c_float, C.c_void_p, C.c_int, C.c_void_p]),
     "sod_allreduce_sgd": (C.c_int, [C.POINTER(sod_comm), C.c_uint64, C.c_uint64, C.c_void_p, C.c_int64,
-                                    C.POINTER(sod_sgd_segment), C.c_int, C.c_float, C.c_void_p, C.c_uint32, C.c_int,
-                                    C.c_void_p]),
+                                    C.POINTER(sod_sgd_segment), C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_void_p]),
     "sod_grad_nonfinite": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
-    "sod_allreduce_f32": (C.c_int, [C.POINTER(sod_comm), C.c_uint64, C.c_int64, C.c_float, C.c_int, C.c_uint32, C.c_int,
-                                    C.c_void_p]),
+    "sod_allreduce_f32": (C.c_int, [C.POINTER(sod_comm), C.c_uint64, C.c_int64, C.c_float, C.c_int, C.c_int, C.c_void_p]),
     "sod_syncbn_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int]),
     "sod_syncbn_exchange_bytes": (C.c_size_t, [C.c_int]),
     "sod_syncbn_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_float,
-                                 C.c_int, C.c_int, C.POINTER(sod_comm), C.c_uint64, C.c_uint32, C.c_void_p, C.c_size_t,
-                                 C.c_int, C.c_void_p]),
+                                 C.c_int, C.c_int, C.POINTER(sod_comm), C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_size_t, C.c_int, C.c_void_p]),
     "sod_syncbn_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
-                                 C.POINTER(sod_comm), C.c_uint64, C.c_uint32, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+                                 C.POINTER(sod_comm), C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
+                                 C.c_void_p]),
 }
 
 EXPORTS = tuple(_PROTOTYPES)

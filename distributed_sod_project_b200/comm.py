@@ -49,6 +49,7 @@ class Arena:
         self.handle = symm.rendezvous(self.buf, self.group.group_name)
         self.buf.zero_()
         self.error_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.block_seq = torch.zeros(4 * 1024, dtype=torch.int32, device=self.device)   # per-block barrier counters
         torch.cuda.synchronize(self.device)
         dist.barrier(self.group)            # every rank's flags are zero before anyone signals
         ptrs = list(self.handle.buffer_ptrs)
@@ -61,9 +62,9 @@ class Arena:
         self.c.arena_bytes = self.nbytes
         self.c.error_flag = self.error_flag.data_ptr()
         self.c.timeout_cycles = int(timeout_s * 1.9e9)
+        self.c.block_seq = self.block_seq.data_ptr()
         self.has_multicast = mc != 0
         self._top = self.flag_bytes
-        self._seq = [0, 0, 0, 0]
 
     # -- allocation --------------------------------------------------------------------------------
     def alloc(self, nbytes: int, align: int = 256) -> int:
@@ -77,10 +78,6 @@ class Arena:
         esz = torch.empty((), dtype=dtype).element_size()
         return self.buf[offset:offset + numel * esz].view(dtype)
 
-    def next_seq(self, channel: int) -> int:
-        self._seq[channel] += 1
-        return self._seq[channel]
-
     @property
     def ref(self):
         return C.byref(self.c)
@@ -92,7 +89,7 @@ class Arena:
 
     # -- plain all-reduce (sweep, scalar mean) -----------------------------------------------------------
     def allreduce_(self, offset: int, numel: int, scale: float = 1.0, algo: int = 0, no_multimem: bool = False):
-        rc = _lib.lib().sod_allreduce_f32(self.ref, offset, numel, float(scale), int(algo), self.next_seq(3),
+        rc = _lib.lib().sod_allreduce_f32(self.ref, offset, numel, float(scale), int(algo),
                                           _lib.SOD_ALGO_NO_MULTIMEM if no_multimem else 0, _lib.stream_ptr())
         _lib.check(rc, "sod_allreduce_f32")
         _lib.count_launch()

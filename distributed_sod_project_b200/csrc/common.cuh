@@ -47,6 +47,13 @@ struct IO<float> {
     }
     __device__ __forceinline__ static float load1(const float* p) { return *p; }
     __device__ __forceinline__ static void store1(float* p, float v) { *p = v; }
+    struct Raw { float4 a, b; };
+    __device__ __forceinline__ static Raw load_raw(const float* p) {
+        Raw r; r.a = *reinterpret_cast<const float4*>(p); r.b = *reinterpret_cast<const float4*>(p + 4); return r;
+    }
+    __device__ __forceinline__ static void unpack(const Raw& r, float (&f)[8]) {
+        f[0] = r.a.x; f[1] = r.a.y; f[2] = r.a.z; f[3] = r.a.w; f[4] = r.b.x; f[5] = r.b.y; f[6] = r.b.z; f[7] = r.b.w;
+    }
 };
 
 template <>
@@ -70,6 +77,16 @@ struct IO<__nv_bfloat16> {
     }
     __device__ __forceinline__ static float load1(const __nv_bfloat16* p) { return __bfloat162float(*p); }
     __device__ __forceinline__ static void store1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+    using Raw = uint4;
+    __device__ __forceinline__ static Raw load_raw(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+    __device__ __forceinline__ static void unpack(const Raw& u, float (&f)[8]) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 t = __bfloat1622float2(h[i]);
+            f[2 * i] = t.x; f[2 * i + 1] = t.y;
+        }
+    }
 };
 
 template <>
@@ -93,6 +110,16 @@ struct IO<__half> {
     }
     __device__ __forceinline__ static float load1(const __half* p) { return __half2float(*p); }
     __device__ __forceinline__ static void store1(__half* p, float v) { *p = __float2half_rn(v); }
+    using Raw = uint4;
+    __device__ __forceinline__ static Raw load_raw(const __half* p) { return *reinterpret_cast<const uint4*>(p); }
+    __device__ __forceinline__ static void unpack(const Raw& u, float (&f)[8]) {
+        const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 t = __half22float2(h[i]);
+            f[2 * i] = t.x; f[2 * i + 1] = t.y;
+        }
+    }
 };
 
 // dtype dispatch: FN is a generic lambda taking a value of the element type as a tag
@@ -215,16 +242,18 @@ struct CommDev {
     uint64_t mc;
     uint32_t* error_flag;
     unsigned long long timeout_cycles;
+    uint32_t* block_seq;
 };
 
 static inline int make_comm_dev(const sod_comm* c, CommDev& d) {
     if (c == nullptr) {
-        d.rank = 0; d.world = 1; d.mc = 0; d.error_flag = nullptr; d.timeout_cycles = 0;
+        d.rank = 0; d.world = 1; d.mc = 0; d.error_flag = nullptr; d.timeout_cycles = 0; d.block_seq = nullptr;
         for (int i = 0; i < SOD_MAX_WORLD; ++i) d.peer[i] = 0;
         return SOD_OK;
     }
     if (c->world < 1 || c->world > SOD_MAX_WORLD || c->rank < 0 || c->rank >= c->world) return SOD_ECOMM;
-    d.rank = c->rank; d.world = c->world; d.mc = c->mc; d.error_flag = c->error_flag;
+    d.rank = c->rank; d.world = c->world; d.mc = c->mc; d.error_flag = c->error_flag; d.block_seq = c->block_seq;
+    if (c->world > 1 && c->block_seq == nullptr) return SOD_ECOMM;
     d.timeout_cycles = c->timeout_cycles ? c->timeout_cycles : 40000000000ull;  // ~20 s at 2 GHz
     for (int i = 0; i < SOD_MAX_WORLD; ++i) d.peer[i] = (i < c->world) ? c->peer[i] : 0;
     for (int i = 0; i < c->world; ++i)
@@ -239,11 +268,19 @@ __device__ __forceinline__ uint32_t* comm_flag(uint64_t arena, int channel, int 
 
 // Barrier between block `block` of every rank on `channel`: on return every peer's block has reached
 // the same call (release/acquire at system scope, so peer writes issued before it are visible).
-// `value` must increase monotonically per (channel, block). Returns false on timeout.
-__device__ __forceinline__ bool comm_block_barrier(const CommDev& c, int channel, int block, uint32_t value) {
+// The sequence number lives in device memory (c.block_seq) and is advanced here, identically on all
+// ranks because every rank issues the same calls with the same grids. Returns false on timeout.
+__device__ __forceinline__ bool comm_block_barrier(const CommDev& c, int channel, int block) {
     __shared__ int s_ok;
-    if (threadIdx.x == 0) s_ok = 1;
+    __shared__ uint32_t s_val;
+    if (threadIdx.x == 0) {
+        s_ok = 1;
+        uint32_t* slot = c.block_seq + channel * SOD_COMM_MAX_BLOCKS + block;
+        s_val = *slot + 1u;
+        *slot = s_val;
+    }
     __syncthreads();
+    const uint32_t value = s_val;
     if (threadIdx.x < static_cast<unsigned>(c.world)) {
         const int peer = threadIdx.x;
         __threadfence_system();

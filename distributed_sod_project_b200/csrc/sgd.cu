@@ -147,10 +147,10 @@ __global__ void __launch_bounds__(kThreads) allreduce_sgd_kernel(const __grid_co
                                                                  uint64_t param_off, float4* __restrict__ mom,
                                                                  long long nvec, const __grid_constant__ SegTable segs,
                                                                  float scale, const uint32_t* found_inf,
-                                                                 uint32_t seq_base, int zero_grad) {
+                                                                 int zero_grad) {
     const bool skip = (found_inf != nullptr && *found_inf != 0);  // caller guarantees identical on all ranks
     // every rank's backward has finished writing its gradients
-    if (!comm_block_barrier(c, 0, blockIdx.x, seq_base + 1)) return;
+    if (!comm_block_barrier(c, 0, blockIdx.x)) return;
 
     const long long shard = (nvec + c.world - 1) / c.world;
     const long long stride = static_cast<long long>(gridDim.x) * kThreads;
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(kThreads) allreduce_sgd_kernel(const __grid_co
         }
     }
     // every rank's parameter shard has landed everywhere (and every peer is done reading my gradients)
-    if (!comm_block_barrier(c, 0, blockIdx.x, seq_base + 2)) return;
+    if (!comm_block_barrier(c, 0, blockIdx.x)) return;
 
     if (zero_grad) {
         // this block's peers read exactly the vectors {q*shard + blockIdx*kThreads + t + k*stride}: safe to clear now
@@ -202,8 +202,8 @@ __global__ void __launch_bounds__(kThreads) allreduce_sgd_kernel(const __grid_co
 // ------------------------------------------------------------------------------------------------
 template <bool kMulticast>
 __global__ void __launch_bounds__(kThreads) allreduce_two_shot_kernel(const __grid_constant__ CommDev c, uint64_t off,
-                                                                      long long nvec, float scale, uint32_t seq_base) {
-    if (!comm_block_barrier(c, 3, blockIdx.x, seq_base + 1)) return;
+                                                                      long long nvec, float scale) {
+    if (!comm_block_barrier(c, 3, blockIdx.x)) return;
     const long long shard = (nvec + c.world - 1) / c.world;
     const long long stride = static_cast<long long>(gridDim.x) * kThreads;
     const long long lo = shard * c.rank;
@@ -224,14 +224,14 @@ __global__ void __launch_bounds__(kThreads) allreduce_two_shot_kernel(const __gr
             }
         }
     }
-    comm_block_barrier(c, 3, blockIdx.x, seq_base + 2);
+    comm_block_barrier(c, 3, blockIdx.x);
 }
 
 // one-shot: every rank reads every peer's whole buffer and keeps the sum locally (latency-optimal for
 // small messages). In place is safe because results are written only after the mid barrier.
 __global__ void __launch_bounds__(kThreads) allreduce_one_shot_kernel(const __grid_constant__ CommDev c, uint64_t off,
-                                                                      long long nvec, float scale, uint32_t seq_base) {
-    if (!comm_block_barrier(c, 3, blockIdx.x, seq_base + 1)) return;
+                                                                      long long nvec, float scale) {
+    if (!comm_block_barrier(c, 3, blockIdx.x)) return;
     const long long stride = static_cast<long long>(gridDim.x) * kThreads;
     const long long first = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x;
     // the host sizes the grid so that each thread owns at most kUnroll vectors → results stay in registers
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(kThreads) allreduce_one_shot_kernel(const __gr
             acc[u].x *= scale; acc[u].y *= scale; acc[u].z *= scale; acc[u].w *= scale;
         }
     }
-    if (!comm_block_barrier(c, 3, blockIdx.x, seq_base + 2)) return;  // everyone has finished reading
+    if (!comm_block_barrier(c, 3, blockIdx.x)) return;  // everyone has finished reading
     float4* local = reinterpret_cast<float4*>(c.peer[c.rank] + off);
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
@@ -296,7 +296,7 @@ extern "C" int sod_grad_nonfinite(const float* grad, int64_t n, uint32_t* found_
 
 extern "C" int sod_allreduce_sgd(const sod_comm* comm, uint64_t grad_off, uint64_t param_off, float* mom, int64_t n,
                                  const sod_sgd_segment* segs, int nseg, float inv_scale, const uint32_t* found_inf,
-                                 uint32_t seq, int flags, void* stream) {
+                                 int flags, void* stream) {
     using namespace sod;
     SOD_CHECK_ARG(comm && mom && n > 0, SOD_EINVAL);
     SOD_CHECK_ARG((n & 3) == 0 && aligned16(mom) && (grad_off & 15) == 0 && (param_off & 15) == 0, SOD_EALIGN);
@@ -317,15 +317,15 @@ extern "C" int sod_allreduce_sgd(const sod_comm* comm, uint64_t grad_off, uint64
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (mc)
         allreduce_sgd_kernel<true><<<grid, kThreads, 0, s>>>(c, grad_off, param_off, reinterpret_cast<float4*>(mom), nvec, t,
-                                                             scale, found_inf, seq * 4u, zg);
+                                                             scale, found_inf, zg);
     else
         allreduce_sgd_kernel<false><<<grid, kThreads, 0, s>>>(c, grad_off, param_off, reinterpret_cast<float4*>(mom), nvec, t,
-                                                              scale, found_inf, seq * 4u, zg);
+                                                              scale, found_inf, zg);
     return static_cast<int>(cudaGetLastError());
 }
 
-extern "C" int sod_allreduce_f32(const sod_comm* comm, uint64_t off, int64_t n, float scale, int algo, uint32_t seq,
-                                 int flags, void* stream) {
+extern "C" int sod_allreduce_f32(const sod_comm* comm, uint64_t off, int64_t n, float scale, int algo, int flags,
+                                 void* stream) {
     using namespace sod;
     SOD_CHECK_ARG(comm && n > 0 && algo >= 0 && algo <= 2, SOD_EINVAL);
     SOD_CHECK_ARG((n & 3) == 0 && (off & 15) == 0, SOD_EALIGN);
@@ -341,12 +341,12 @@ extern "C" int sod_allreduce_f32(const sod_comm* comm, uint64_t off, int64_t n, 
     if (algo == 1 && nvec > one_shot_cap) return SOD_EUNSUPPORTED;
     if (algo == 1) {
         const unsigned grid = comm_grid(nvec);
-        allreduce_one_shot_kernel<<<grid, kThreads, 0, s>>>(c, off, nvec, scale, seq * 4u);
+        allreduce_one_shot_kernel<<<grid, kThreads, 0, s>>>(c, off, nvec, scale);
     } else {
         const unsigned grid = comm_grid((nvec + c.world - 1) / c.world);
         const bool mc = (c.mc != 0) && !(flags & SOD_ALGO_NO_MULTIMEM);
-        if (mc) allreduce_two_shot_kernel<true><<<grid, kThreads, 0, s>>>(c, off, nvec, scale, seq * 4u);
-        else allreduce_two_shot_kernel<false><<<grid, kThreads, 0, s>>>(c, off, nvec, scale, seq * 4u);
+        if (mc) allreduce_two_shot_kernel<true><<<grid, kThreads, 0, s>>>(c, off, nvec, scale);
+        else allreduce_two_shot_kernel<false><<<grid, kThreads, 0, s>>>(c, off, nvec, scale);
     }
     return static_cast<int>(cudaGetLastError());
 }

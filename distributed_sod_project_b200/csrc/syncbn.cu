@@ -7,19 +7,25 @@
 // bound collectives per layer per direction, 84 layers.  Arithmetic spec (readable in-container
 // equivalent): torch/nn/modules/_functions.py:7-209.
 //
-// Layout: channels-last matrix [rows = N·H·W, C].  A CTA owns a (slab of ≤256 channels) × (strip of
-// rows).  Each thread owns 8 consecutive channels (one 16-byte packet for 16-bit data) and walks rows.
+// Layout: channels-last matrix [rows = N·H·W, C].  One persistent CTA per SM owns a contiguous strip
+// of rows (= a contiguous byte range), every thread owns one fixed group of 8 channels.
 //
-//   phase 1  per-thread fp32 (Σ, Σ²) → warp shuffles → shared memory → one partial per CTA in L2;
-//            the LAST CTA of a slab to arrive (atomic ticket) sums the slab's partials in fixed order
-//            and publishes the LOCAL totals to every rank: 8-byte {value, tag} packets written with
-//            multimem.st (NVLS multicast: one store, the switch replicates) or per-peer stores.
-//   phase 2  every CTA of every rank spins on the {value, tag} packets of its slab in ITS OWN memory
-//            (no flag round trip, no fence: an 8-byte store is single-copy atomic), adds the W
-//            contributions in rank order (bit-identical on all ranks), derives mean / invstd, and
-//            normalizes its strip, which it just read and which is still in L1/L2.
-// The same packet mechanism is the intra-GPU broadcast when world == 1, so there is no grid barrier.
-// All CTAs must be co-resident: the host caps the grid at (SMs × occupancy).  Every spin is bounded.
+//   stage   the strip is pulled through a ring of shared-memory stages by 1-D bulk async copies
+//           (TMA engine, mbarrier completion): ≈180 KB per SM in flight with no registers tied up;
+//   phase 1 per-thread fp32 partial sums straight from shared memory → CTA total [2C];
+//   hop 1   the CTA total is written as 8-byte {value, tag} packets; CTA b then owns a slice of the
+//           2C entries, waits for the packets of all CTAs (spins on the tag — an 8-byte store is
+//           single-copy atomic, so there is no flag, no fence, no atomic, no counter to reset), sums
+//           them in CTA order and
+//   hop 2   publishes the GPU-local totals as packets to EVERY rank's exchange slot: multimem.st on the
+//           NVLS multicast mapping (one store, the switch replicates) or per-peer stores;
+//   phase 2 every CTA of every rank sums the W per-rank packets in rank order (bit-identical
+//           statistics everywhere), derives the per-channel coefficients and normalizes its strip —
+//           the last ring-full of the strip is still resident in shared memory and is NOT re-read;
+//           only the part of the strip that did not fit streams through the ring again (from L2).
+// world == 1 uses the same packet mechanism for the intra-GPU broadcast, so there is no grid barrier.
+// All CTAs must be co-resident (grid ≤ #SMs, 1 CTA/SM). Every spin is bounded; a timeout sets
+// comm->error_flag and lets the kernel run to completion (outstanding bulk copies must land).
 #include "common.cuh"
 
 namespace sod {
@@ -27,18 +33,24 @@ namespace {
 
 constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
-constexpr int kSlabMax = 256;  // channels per slab → at most 32 lanes of 8 channels
-constexpr int kMaxSlabs = 64;
+constexpr int kMaxC = 2048;
+constexpr int kMaxStages = 16;
+constexpr int kMaxStreams = 4;
+constexpr int kMaxGrid = 160;
+constexpr int kSmemFixed = 256 /*barriers*/ + 32768 /*red*/ + 3 * kMaxC * 4 /*coefficients*/;
 
 struct BnGeom {
-    int C, slabC, L, R, slabs, strips;
-    long long rows, rows_per_strip;
+    int C, es, L;                // channels, element bytes, lanes (= C/8 packets per row)
+    int chunk_bytes;             // per stream per chunk
+    int chunk_rows, ppt;         // rows per chunk, packets per thread per chunk
+    int nstream, nstage;
+    int strips, chunks_per_strip;
+    long long rows, total_chunks;
 };
 
 struct BnWork {
-    unsigned* counters;  // [kMaxSlabs]
-    float* partials;     // [slabs][strips][16*L]
-    uint2* ll_local;     // [2C] packets, used when world == 1
+    uint2* partials;   // [strips][2C] packets
+    uint2* ll_local;   // [2C] packets, exchange slot when world == 1
 };
 
 struct BnFwd {
@@ -46,6 +58,7 @@ struct BnFwd {
     void* y;
     const float *gamma, *beta;
     float *rmean, *rvar, *smean, *sinvstd;
+    long long* nbt;  // num_batches_tracked (+= 1) or null
     float momentum, eps;
     int relu, training;
     BnGeom g;
@@ -53,6 +66,7 @@ struct BnFwd {
     CommDev c;
     uint64_t stats_off;
     uint32_t tag;
+    const uint32_t* epoch;
     int use_mc;
 };
 
@@ -67,203 +81,310 @@ struct BnBwd {
     CommDev c;
     uint64_t stats_off;
     uint32_t tag;
+    const uint32_t* epoch;
     int use_mc;
 };
 
-// ---- packet exchange ---------------------------------------------------------------------------------
-// entry index space of one layer call: [src_rank][2C]; within a slab the order is j = k*L + l with
-// k in [0,16): k<8 → first statistic of channel l*8+k, k>=8 → second statistic of channel l*8+(k-8).
-__device__ __forceinline__ void publish(const CommDev& c, int use_mc, uint64_t stats_off, uint2* ll_local, int C,
-                                        int entry, float value, uint32_t tag) {
-    const uint32_t bits = __float_as_uint(value);
+// tag of this call: host counter (eager) or device epoch + call index (CUDA-graph replay)
+__device__ __forceinline__ uint32_t call_tag(uint32_t seq, const uint32_t* epoch) {
+    return epoch ? (0x80000000u | ((*epoch & 0x1FFFFFu) << 10) | (seq & 1023u)) : (seq & 0x7FFFFFFFu);
+}
+
+// ---- packets -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_packet_gpu(uint2* p, float v, uint32_t tag) {
+    asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ uint2 ld_packet_gpu(const uint2* p) {
+    uint2 v;
+    asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float wait_packet_gpu(const uint2* p, uint32_t tag, unsigned long long timeout, int& fail) {
+    uint2 v = ld_packet_gpu(p);
+    if (v.y != tag) {
+        const long long t0 = clock64();
+        do {
+            v = ld_packet_gpu(p);
+            if (static_cast<unsigned long long>(clock64() - t0) > timeout) { fail = 1; return 0.f; }
+        } while (v.y != tag);
+    }
+    return __uint_as_float(v.x);
+}
+__device__ __forceinline__ float wait_packet_sys(const void* p, uint32_t tag, unsigned long long timeout, int& fail) {
+    uint2 v = ld_relaxed_sys_v2(p);
+    if (v.y != tag) {
+        const long long t0 = clock64();
+        do {
+            v = ld_relaxed_sys_v2(p);
+            if (static_cast<unsigned long long>(clock64() - t0) > timeout) { fail = 1; return 0.f; }
+        } while (v.y != tag);
+    }
+    return __uint_as_float(v.x);
+}
+
+// hop 2: GPU-local total of entry `entry` → every rank's exchange slot [src_rank][2C]
+__device__ __forceinline__ void publish(const CommDev& c, int use_mc, uint64_t stats_off, uint2* ll_local, int C, int entry,
+                                        float value, uint32_t tag) {
     if (c.world == 1) {
-        st_relaxed_sys_v2(ll_local + entry, bits, tag);
+        st_packet_gpu(ll_local + entry, value, tag);
         return;
     }
     const uint64_t off = stats_off + (static_cast<uint64_t>(c.rank) * 2u * C + entry) * 8u;
+    const uint32_t bits = __float_as_uint(value);
     if (use_mc) {
         multimem_st_b64(reinterpret_cast<void*>(c.mc + off), bits, tag);
     } else {
         for (int q = 0; q < c.world; ++q) st_relaxed_sys_v2(reinterpret_cast<void*>(c.peer[q] + off), bits, tag);
     }
 }
-
-// sum over ranks (rank order) of entry `entry`; false on timeout
-__device__ __forceinline__ bool collect(const CommDev& c, uint64_t stats_off, const uint2* ll_local, int C, int entry,
-                                        uint32_t tag, unsigned long long timeout, float& out) {
+__device__ __forceinline__ float collect(const CommDev& c, uint64_t stats_off, const uint2* ll_local, int C, int entry,
+                                         uint32_t tag, unsigned long long timeout, int& fail) {
+    if (c.world == 1) return wait_packet_gpu(ll_local + entry, tag, timeout, fail);
     float acc = 0.f;
-    const long long t0 = clock64();
-    for (int q = 0; q < c.world; ++q) {
-        const void* p = (c.world == 1)
-                            ? static_cast<const void*>(ll_local + entry)
-                            : reinterpret_cast<const void*>(c.peer[c.rank] + stats_off +
-                                                            (static_cast<uint64_t>(q) * 2u * C + entry) * 8u);
-        uint2 v = ld_relaxed_sys_v2(p);
-        while (v.y != tag) {
-            if (static_cast<unsigned long long>(clock64() - t0) > timeout) return false;
-            v = ld_relaxed_sys_v2(p);
-        }
-        acc += __uint_as_float(v.x);
-    }
-    out = acc;
-    return true;
+    for (int q = 0; q < c.world; ++q)  // rank order: identical sum on every rank
+        acc += wait_packet_sys(reinterpret_cast<const void*>(c.peer[c.rank] + stats_off + (static_cast<uint64_t>(q) * 2u * C + entry) * 8u),
+                               tag, timeout, fail);
+    return acc;
 }
 
-// ---- CTA-level reduction of 16 per-thread accumulators over the row-lanes --------------------------
-// on return threads j < 16*L hold (in `out`) the CTA total of entry j = k*L + l
-__device__ __forceinline__ float cta_reduce16(float (&a)[16], int L, float* red /*[kWarps][16*L]*/) {
+// ---- shared-memory ring ---------------------------------------------------------------------------------
+struct Ring {
+    uint64_t* full;
+    uint64_t* empty;
+    unsigned char* stages;
+    int nstage, nstream, chunk_bytes;
+    uint32_t full_par, empty_par;  // bit s = parity of the next completion to wait for
+
+    __device__ __forceinline__ unsigned char* buf(int s, int k) const {
+        return stages + (static_cast<size_t>(s) * nstream + k) * chunk_bytes;
+    }
+    __device__ __forceinline__ void wait_full(int s) {
+        mbar_wait(&full[s], (full_par >> s) & 1u);
+        full_par ^= 1u << s;
+    }
+    // called by every thread after it has finished reading stage s, when the stage is going to be refilled
+    __device__ __forceinline__ void release(int s) {
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0)
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[s])) : "memory");
+    }
+    // thread 0 only
+    __device__ __forceinline__ void wait_empty(int s) {
+        mbar_wait(&empty[s], (empty_par >> s) & 1u);
+        empty_par ^= 1u << s;
+    }
+};
+
+struct StripInfo {
+    long long chunk0;   // first chunk index of this strip
+    int n;              // number of chunks in this strip
+};
+
+__device__ __forceinline__ StripInfo strip_info(const BnGeom& g) {
+    StripInfo s;
+    s.chunk0 = static_cast<long long>(blockIdx.x) * g.chunks_per_strip;
+    long long rem = g.total_chunks - s.chunk0;
+    s.n = static_cast<int>(rem < g.chunks_per_strip ? rem : g.chunks_per_strip);
+    return s;
+}
+__device__ __forceinline__ int chunk_rows_of(const BnGeom& g, long long chunk) {
+    const long long r0 = chunk * g.chunk_rows;
+    const long long rem = g.rows - r0;
+    return static_cast<int>(rem < g.chunk_rows ? rem : g.chunk_rows);
+}
+
+// thread 0: start the bulk copies of `chunk` (all streams) into stage s
+template <int NS>
+__device__ __forceinline__ void issue_chunk(Ring& ring, const BnGeom& g, const void* const (&src)[NS], int s, long long chunk) {
+    const uint32_t bytes = static_cast<uint32_t>(chunk_rows_of(g, chunk)) * g.C * g.es;
+    const size_t off = static_cast<size_t>(chunk) * g.chunk_rows * g.C * g.es;
+    int active = 0;
+#pragma unroll
+    for (int k = 0; k < NS; ++k) active += (src[k] != nullptr);
+    mbar_arrive_expect_tx(&ring.full[s], bytes * active);
+#pragma unroll
+    for (int k = 0; k < NS; ++k)
+        if (src[k] != nullptr) bulk_g2s(ring.buf(s, k), static_cast<const char*>(src[k]) + off, bytes, &ring.full[s]);
+}
+
+// ---- CTA-level reduction of 16 per-thread accumulators over the threads that share a lane -----------------
+// on return `red[j]`, j = k*L + l  (k<8: first statistic of channel l*8+k, k>=8: second statistic), holds the CTA total
+__device__ __forceinline__ void cta_reduce16(float (&a)[16], int L, float* red /*[8192]*/) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        float v = a[k];
-        for (int o = 16; o >= L; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        a[k] = v;
-    }
     const int n16 = 16 * L;
-    if (lane < L) {
+    if (L <= 32) {
+        // threads with equal (lane % L) inside a warp share a channel group: butterfly over the row-lanes
 #pragma unroll
-        for (int k = 0; k < 16; ++k) red[warp * n16 + k * L + lane] = a[k];
+        for (int k = 0; k < 16; ++k) {
+            float v = a[k];
+            for (int o = 16; o >= L; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            a[k] = v;
+        }
+        if (lane < L) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) red[warp * n16 + k * L + lane] = a[k];
+        }
+        __syncthreads();
+        float tot = 0.f;
+        if (tid < n16) {
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) tot += red[w * n16 + tid];
+        }
+        __syncthreads();
+        if (tid < n16) red[tid] = tot;
+    } else {
+        // L in {64,128,256}: thread tid owns lane l = tid % L; R = kThreads / L threads share it
+        const int l = tid % L, r = tid / L, R = kThreads / L;
+        // two rounds of 8 statistics so that the scratch stays within 32 KB: [R][8][L] floats = 16 KB
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 8; ++k) red[4096 + (r * 8 + k) * L + l] = a[half * 8 + k];
+            __syncthreads();
+            for (int j = tid; j < 8 * L; j += kThreads) {
+                float tot = 0.f;
+                for (int rr = 0; rr < R; ++rr) tot += red[4096 + rr * 8 * L + j];
+                red[half * 8 * L + j] = tot;  // j = k*L + l
+            }
+        }
     }
     __syncthreads();
-    float tot = 0.f;
-    if (tid < n16) {
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) tot += red[w * n16 + tid];
-    }
-    return tot;
 }
 
-// Writes this CTA's partial, takes a ticket, and if last of its slab: reduces the slab's partials in
-// fixed order. Returns true for the finisher, whose threads j < 16L then hold the slab total in `tot`.
-__device__ __forceinline__ bool slab_finish(const BnGeom& g, const BnWork& w, int slab, int strip, float* red,
-                                            float& tot) {
-    __shared__ int s_last;
-    const int tid = threadIdx.x;
+// hop 1 + hop 2 (+ optional per-entry side effect through `on_total`), then collect into red[0..n16)
+template <typename F>
+__device__ __forceinline__ void exchange(const BnGeom& g, const BnWork& w, const CommDev& c, int use_mc, uint64_t stats_off,
+                                         uint32_t tag, float* red, int* s_fail, F on_total) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n16 = 16 * g.L;
-    float* mine = w.partials + (static_cast<size_t>(slab) * g.strips + strip) * n16;
-    if (g.strips == 1) return true;  // tot already is the slab total
-    if (tid < n16) mine[tid] = tot;
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        const unsigned t = atomicAdd(&w.counters[slab], 1u);
-        s_last = (t == static_cast<unsigned>(g.strips - 1));
-        if (s_last) w.counters[slab] = 0;  // everyone has arrived; ready for the next launch
+    const int strips = static_cast<int>(gridDim.x);
+    const unsigned long long timeout = c.timeout_cycles ? c.timeout_cycles : 4000000000ull;
+    int fail = 0;
+    // hop 1a: my CTA total as packets
+    uint2* mine = w.partials + static_cast<size_t>(blockIdx.x) * n16;
+    for (int j = tid; j < n16; j += kThreads) st_packet_gpu(mine + j, red[j], tag);
+    // hop 1b: my slice of entries, summed over all CTAs in CTA order (one warp per entry)
+    const int per = (n16 + strips - 1) / strips;
+    const int j0 = blockIdx.x * per;
+    const int j1 = (j0 + per < n16) ? j0 + per : n16;
+    for (int j = j0 + warp; j < j1; j += kWarps) {
+        float acc = 0.f;
+        for (int t = lane; t < strips; t += 32) acc += wait_packet_gpu(w.partials + static_cast<size_t>(t) * n16 + j, tag, timeout, fail);
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            on_total(j, acc);
+            publish(c, use_mc, stats_off, w.ll_local, g.C, j, acc, tag);  // hop 2
+        }
+    }
+    __syncthreads();  // everyone has finished reading red[] (hop 1a) before it is overwritten
+    for (int j = tid; j < n16; j += kThreads) red[j] = collect(c, stats_off, w.ll_local, g.C, j, tag, timeout, fail);
+    if (fail) {
+        *s_fail = 1;
+        if (c.error_flag) atomicExch(c.error_flag, 0xDEAD0001u);
     }
     __syncthreads();
-    if (!s_last) return false;
-    __threadfence();
-    // parts × n16 threads, each sums a residue class of strips; then a fixed-order combine
-    const int parts = kThreads / n16;  // ≥ 1 (n16 ≤ 512)
-    const int j = tid % n16, part = tid / n16;
-    float acc = 0.f;
-    if (part < parts) {
-        const float* base = w.partials + static_cast<size_t>(slab) * g.strips * n16 + j;
-        for (int t = part; t < g.strips; t += parts) acc += __ldcg(base + static_cast<size_t>(t) * n16);
+}
+
+__device__ __forceinline__ void ring_setup(Ring& ring, unsigned char* smem, const BnGeom& g, int nstream) {
+    ring.full = reinterpret_cast<uint64_t*>(smem);
+    ring.empty = ring.full + kMaxStages;
+    ring.stages = smem + kSmemFixed;
+    ring.nstage = g.nstage;
+    ring.nstream = nstream;
+    ring.chunk_bytes = g.chunk_bytes;
+    ring.full_par = 0;
+    ring.empty_par = 0;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < g.nstage; ++s) {
+            mbar_init(&ring.full[s], 1);
+            mbar_init(&ring.empty[s], kWarps);
+        }
+        mbar_fence_init();
     }
-    __syncthreads();  // red is free again (cta_reduce16 readers are done: they passed the barriers above)
-    if (part < parts) red[part * n16 + j] = acc;
     __syncthreads();
-    tot = 0.f;
-    if (tid < n16)
-        for (int p = 0; p < parts; ++p) tot += red[p * n16 + tid];
-    return true;
 }
 
 // =================================================================================================
 // forward
 // =================================================================================================
 template <typename T>
-__global__ void __launch_bounds__(kThreads) syncbn_fwd_kernel(const __grid_constant__ BnFwd prm) {
-    __shared__ float red[kWarps * 16 * 32];  // 32 KB
-    __shared__ float s_scale[kSlabMax], s_shift[kSlabMax];
+__global__ void __launch_bounds__(kThreads, 1) syncbn_fwd_kernel(const __grid_constant__ BnFwd prm) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    float* red = reinterpret_cast<float*>(smem + 256);
+    float* s_scale = reinterpret_cast<float*>(smem + 256 + 32768);
+    float* s_shift = s_scale + kMaxC;
     __shared__ int s_fail;
 
     const BnGeom& g = prm.g;
     const int tid = threadIdx.x;
-    const int L = g.L, R = g.R, C = g.C;
-    const int l = tid % L, rl = tid / L;
-    const int slab = blockIdx.x % g.slabs, strip = blockIdx.x / g.slabs;
-    const long long r0 = strip * g.rows_per_strip;
-    const long long r1 = (r0 + g.rows_per_strip < g.rows) ? r0 + g.rows_per_strip : g.rows;
-    const size_t coff = static_cast<size_t>(slab) * g.slabC + static_cast<size_t>(l) * 8;
-    const T* __restrict__ x = static_cast<const T*>(prm.x);
-    const T* __restrict__ pre = static_cast<const T*>(prm.pre);
-    const T* __restrict__ res = static_cast<const T*>(prm.res);
-    T* __restrict__ y = static_cast<T*>(prm.y);
-    const int n16 = 16 * L;
+    const int L = g.L, C = g.C;
+    const int l = tid % L;
+    const StripInfo sp = strip_info(g);
+    const int NS = g.nstage;
+    const bool has_pre = prm.pre != nullptr;
+    const T* __restrict__ gres = static_cast<const T*>(prm.res);
+    T* __restrict__ gy = static_cast<T*>(prm.y);
     if (tid == 0) s_fail = 0;
 
+    Ring ring;
+    ring_setup(ring, smem, g, has_pre ? 2 : 1);
+    const void* const src[2] = {prm.x, prm.pre};
+    if (tid == 0) {
+        const int first = sp.n < NS ? sp.n : NS;
+        for (int i = 0; i < first; ++i) issue_chunk<2>(ring, g, src, i, sp.chunk0 + i);
+    }
+
     if (prm.training) {
-        // ---- phase 1 ---------------------------------------------------------------------------------
+        // ---- phase 1: Σz, Σz² from shared memory ----------------------------------------------------------
         float a[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) a[k] = 0.f;
-        long long r = r0 + rl;
-        for (; r + 3ll * R < r1; r += 4ll * R) {
-            float z[4][8];
+        for (int i = 0; i < sp.n; ++i) {
+            const int s = i % NS;
+            ring.wait_full(s);
+            const int npk = chunk_rows_of(g, sp.chunk0 + i) * L;
+            const T* xs = reinterpret_cast<const T*>(ring.buf(s, 0));
+            const T* ps = reinterpret_cast<const T*>(ring.buf(s, 1));
+            for (int j = 0; j < g.ppt; ++j) {
+                const int q = tid + j * kThreads;
+                if (q < npk) {
+                    float z[8];
+                    IO<T>::load8(xs + q * 8, z);
+                    if (has_pre) {
+                        float t[8];
+                        IO<T>::load8(ps + q * 8, t);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) IO<T>::load8(x + (r + static_cast<long long>(u) * R) * C + coff, z[u]);
-            if (pre) {
+                        for (int k = 0; k < 8; ++k) z[k] += t[k];
+                    }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    float t[8];
-                    IO<T>::load8(pre + (r + static_cast<long long>(u) * R) * C + coff, t);
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) z[u][k] += t[k];
+                    for (int k = 0; k < 8; ++k) {
+                        a[k] += z[k];
+                        a[8 + k] = fmaf(z[k], z[k], a[8 + k]);
+                    }
                 }
             }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    a[k] += z[u][k];
-                    a[8 + k] = fmaf(z[u][k], z[u][k], a[8 + k]);
+            if (i + NS < sp.n) {  // the strip is longer than the ring: recycle this stage
+                ring.release(s);
+                if (tid == 0) {
+                    ring.wait_empty(s);
+                    issue_chunk<2>(ring, g, src, s, sp.chunk0 + i + NS);
                 }
-        }
-        for (; r < r1; r += R) {
-            float z[8];
-            IO<T>::load8(x + r * C + coff, z);
-            if (pre) {
-                float t[8];
-                IO<T>::load8(pre + r * C + coff, t);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) z[k] += t[k];
-            }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                a[k] += z[k];
-                a[8 + k] = fmaf(z[k], z[k], a[8 + k]);
             }
         }
-        float tot = cta_reduce16(a, L, red);
-        if (slab_finish(g, prm.w, slab, strip, red, tot)) {
-            if (tid < n16) publish(prm.c, prm.use_mc, prm.stats_off, prm.w.ll_local, C, slab * n16 + tid, tot, prm.tag);
-        }
-        // ---- phase 2a: global statistics -------------------------------------------------------------
-        __syncthreads();
-        if (tid < n16) {
-            float v;
-            if (!collect(prm.c, prm.stats_off, prm.w.ll_local, C, slab * n16 + tid, prm.tag,
-                         prm.c.timeout_cycles ? prm.c.timeout_cycles : 4000000000ull, v)) {
-                s_fail = 1;
-                if (prm.c.error_flag) atomicExch(prm.c.error_flag, 0xDEAD0001u);
-                v = 0.f;
-            }
-            red[tid] = v;
-        }
-        __syncthreads();
-        if (s_fail) return;
-        if (tid < g.slabC) {
-            const int cl = tid, ll = cl >> 3, k = cl & 7, ch = slab * g.slabC + cl;
-            const float n = static_cast<float>(g.rows) * static_cast<float>(prm.c.world);
+        cta_reduce16(a, L, red);
+        exchange(g, prm.w, prm.c, prm.use_mc, prm.stats_off, call_tag(prm.tag, prm.epoch), red, &s_fail, [](int, float) {});
+        // ---- per-channel coefficients --------------------------------------------------------------------
+        const float n = static_cast<float>(g.rows) * static_cast<float>(prm.c.world);
+        for (int ch = tid; ch < C; ch += kThreads) {
+            const int ll = ch >> 3, k = ch & 7;
             const float mean = red[k * L + ll] / n;
             const float var = fmaxf(red[(8 + k) * L + ll] / n - mean * mean, 0.f);
             const float invstd = 1.0f / sqrtf(var + prm.eps);
             const float sc = invstd * prm.gamma[ch];
-            s_scale[cl] = sc;
-            s_shift[cl] = prm.beta[ch] - mean * sc;
-            if (strip == 0) {
+            s_scale[ch] = sc;
+            s_shift[ch] = prm.beta[ch] - mean * sc;
+            if (blockIdx.x == 0) {
                 prm.smean[ch] = mean;
                 prm.sinvstd[ch] = invstd;
                 if (prm.rmean) {
@@ -273,18 +394,18 @@ __global__ void __launch_bounds__(kThreads) syncbn_fwd_kernel(const __grid_const
                 }
             }
         }
+        if (blockIdx.x == 0 && tid == 0 && prm.nbt) *prm.nbt += 1;
     } else {
-        if (tid < g.slabC) {
-            const int ch = slab * g.slabC + tid;
+        for (int ch = tid; ch < C; ch += kThreads) {
             const float invstd = 1.0f / sqrtf(prm.rvar[ch] + prm.eps);
             const float sc = invstd * prm.gamma[ch];
-            s_scale[tid] = sc;
-            s_shift[tid] = prm.beta[ch] - prm.rmean[ch] * sc;
+            s_scale[ch] = sc;
+            s_shift[ch] = prm.beta[ch] - prm.rmean[ch] * sc;
         }
     }
     __syncthreads();
 
-    // ---- phase 2b: normalize / affine / residual / ReLU over the same strip -------------------------
+    // ---- phase 2: normalize; resident chunks first, then the part of the strip that did not fit ---------
     float sc[8], sh[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -292,64 +413,78 @@ __global__ void __launch_bounds__(kThreads) syncbn_fwd_kernel(const __grid_const
         sh[k] = s_shift[l * 8 + k];
     }
     const bool relu = prm.relu != 0;
-    long long r = r0 + rl;
-    for (; r + 3ll * R < r1; r += 4ll * R) {
-        float z[4][8];
+    const int nres0 = prm.training ? (sp.n > NS ? sp.n - NS : 0) : 0;  // first resident chunk
+    const int nresident = prm.training ? sp.n - nres0 : 0;
+    // processing order: resident chunks first, then the streamed ones
+    auto chunk_of = [&](int i2) -> int {
+        if (!prm.training) return i2;
+        return i2 >= nresident ? nres0 - 1 - (i2 - nresident) : nres0 + i2;
+    };
+    // the residual is read straight from global memory, one chunk ahead, so its latency hides behind the math
+    constexpr int kPptMax = 2;
+    typename IO<T>::Raw rcur[kPptMax], rnext[kPptMax];
+    auto fetch_res = [&](int i2, typename IO<T>::Raw (&dst)[kPptMax]) {
+        if (gres == nullptr || i2 >= sp.n) return;
+        const long long chunk = sp.chunk0 + chunk_of(i2);
+        const int npk = chunk_rows_of(g, chunk) * L;
+        const size_t ebase = static_cast<size_t>(chunk) * g.chunk_rows * C;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) IO<T>::load8(x + (r + static_cast<long long>(u) * R) * C + coff, z[u]);
-        if (pre) {
+        for (int j = 0; j < kPptMax; ++j) {
+            const int q = tid + j * kThreads;
+            if (j < g.ppt && q < npk) dst[j] = IO<T>::load_raw(gres + ebase + static_cast<size_t>(q) * 8);
+        }
+    };
+    fetch_res(0, rcur);
+    for (int i2 = 0; i2 < sp.n; ++i2) {
+        const int c = chunk_of(i2);
+        const bool streamed = prm.training ? (i2 >= nresident) : true;
+        const int s = prm.training ? (nres0 + i2) % NS : i2 % NS;
+        fetch_res(i2 + 1, rnext);
+        if (streamed) ring.wait_full(s);
+        const long long chunk = sp.chunk0 + c;
+        const int npk = chunk_rows_of(g, chunk) * L;
+        const T* xs = reinterpret_cast<const T*>(ring.buf(s, 0));
+        const T* ps = reinterpret_cast<const T*>(ring.buf(s, 1));
+        const size_t ebase = static_cast<size_t>(chunk) * g.chunk_rows * C;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                float t[8];
-                IO<T>::load8(pre + (r + static_cast<long long>(u) * R) * C + coff, t);
+        for (int j = 0; j < kPptMax; ++j) {
+            const int q = tid + j * kThreads;
+            if (j < g.ppt && q < npk) {
+                float z[8];
+                IO<T>::load8(xs + q * 8, z);
+                if (has_pre) {
+                    float t[8];
+                    IO<T>::load8(ps + q * 8, t);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) z[u][k] += t[k];
+                    for (int k = 0; k < 8; ++k) z[k] += t[k];
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) z[k] = fmaf(z[k], sc[k], sh[k]);
+                if (gres) {
+                    float t[8];
+                    IO<T>::unpack(rcur[j], t);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) z[k] += t[k];
+                }
+                if (relu) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) z[k] = fmaxf(z[k], 0.f);
+                }
+                IO<T>::store8(gy + ebase + static_cast<size_t>(q) * 8, z);
             }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-            for (int k = 0; k < 8; ++k) z[u][k] = fmaf(z[u][k], sc[k], sh[k]);
-        if (res) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                float t[8];
-                IO<T>::load8(res + (r + static_cast<long long>(u) * R) * C + coff, t);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) z[u][k] += t[k];
+        for (int j = 0; j < kPptMax; ++j) rcur[j] = rnext[j];
+        // refill: training → the i2-th freed stage takes streamed chunk i2; eval → plain ring
+        const int next = prm.training ? i2 : i2 + NS;
+        const bool more = prm.training ? (i2 < nres0) : (next < sp.n);
+        if (more) {
+            ring.release(s);
+            if (tid == 0) {
+                ring.wait_empty(s);
+                issue_chunk<2>(ring, g, src, s, sp.chunk0 + (prm.training ? nres0 - 1 - next : next));
             }
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (relu) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) z[u][k] = fmaxf(z[u][k], 0.f);
-            }
-            IO<T>::store8(y + (r + static_cast<long long>(u) * R) * C + coff, z[u]);
-        }
-    }
-    for (; r < r1; r += R) {
-        float z[8];
-        IO<T>::load8(x + r * C + coff, z);
-        if (pre) {
-            float t[8];
-            IO<T>::load8(pre + r * C + coff, t);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) z[k] += t[k];
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) z[k] = fmaf(z[k], sc[k], sh[k]);
-        if (res) {
-            float t[8];
-            IO<T>::load8(res + r * C + coff, t);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) z[k] += t[k];
-        }
-        if (relu) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) z[k] = fmaxf(z[k], 0.f);
-        }
-        IO<T>::store8(y + r * C + coff, z);
     }
 }
 
@@ -357,113 +492,119 @@ __global__ void __launch_bounds__(kThreads) syncbn_fwd_kernel(const __grid_const
 // backward
 // =================================================================================================
 template <typename T>
-__global__ void __launch_bounds__(kThreads) syncbn_bwd_kernel(const __grid_constant__ BnBwd prm) {
-    __shared__ float red[kWarps * 16 * 32];
-    __shared__ float s_a[kSlabMax], s_b[kSlabMax], s_d[kSlabMax];
+__global__ void __launch_bounds__(kThreads, 1) syncbn_bwd_kernel(const __grid_constant__ BnBwd prm) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    float* red = reinterpret_cast<float*>(smem + 256);
+    float* s_a = reinterpret_cast<float*>(smem + 256 + 32768);
+    float* s_b = s_a + kMaxC;
+    float* s_d = s_b + kMaxC;
     __shared__ int s_fail;
 
     const BnGeom& g = prm.g;
     const int tid = threadIdx.x;
-    const int L = g.L, R = g.R, C = g.C;
-    const int l = tid % L, rl = tid / L;
-    const int slab = blockIdx.x % g.slabs, strip = blockIdx.x / g.slabs;
-    const long long r0 = strip * g.rows_per_strip;
-    const long long r1 = (r0 + g.rows_per_strip < g.rows) ? r0 + g.rows_per_strip : g.rows;
-    const size_t coff = static_cast<size_t>(slab) * g.slabC + static_cast<size_t>(l) * 8;
-    const int ch0 = slab * g.slabC + l * 8;
-    const T* __restrict__ dy = static_cast<const T*>(prm.dy);
-    const T* __restrict__ x = static_cast<const T*>(prm.x);
-    const T* __restrict__ pre = static_cast<const T*>(prm.pre);
-    const T* __restrict__ yy = static_cast<const T*>(prm.y);
-    T* __restrict__ dz = static_cast<T*>(prm.dz);
-    T* __restrict__ dres = static_cast<T*>(prm.dres);
-    const int n16 = 16 * L;
+    const int L = g.L, C = g.C;
+    const int l = tid % L;
+    const StripInfo sp = strip_info(g);
+    const int NS = g.nstage;
+    const bool has_pre = prm.pre != nullptr;
     const bool relu = prm.relu != 0;
+    T* __restrict__ gdz = static_cast<T*>(prm.dz);
+    T* __restrict__ gdres = static_cast<T*>(prm.dres);
     if (tid == 0) s_fail = 0;
+
+    Ring ring;
+    ring_setup(ring, smem, g, g.nstream);
+    // stream slots: 0 dy, 1 x, then pre (if any), then y (if relu)
+    const int k_pre = 2, k_y = has_pre ? 3 : 2;
+    const void* src[4] = {prm.dy, prm.x, nullptr, nullptr};
+    if (has_pre) src[k_pre] = prm.pre;
+    if (relu) src[k_y] = prm.y;
+    const void* const csrc[4] = {src[0], src[1], src[2], src[3]};
+    if (tid == 0) {
+        const int first = sp.n < NS ? sp.n : NS;
+        for (int i = 0; i < first; ++i) issue_chunk<4>(ring, g, csrc, i, sp.chunk0 + i);
+    }
 
     float mean[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) mean[k] = prm.smean[ch0 + k];
+    for (int k = 0; k < 8; ++k) mean[k] = prm.smean[l * 8 + k];
 
-    // ---- phase 1: Σ dy_m and Σ dy_m (z - mean) ----------------------------------------------------------
+    // ---- phase 1: Σ dy_m and Σ dy_m (z - mean) -------------------------------------------------------------
     float a[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) a[k] = 0.f;
-    for (long long r = r0 + rl; r < r1; r += 2ll * R) {
-        float d[2][8], z[2][8];
-        bool ok[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const long long rr = r + static_cast<long long>(u) * R;
-            ok[u] = rr < r1;
-            if (ok[u]) {
-                IO<T>::load8(dy + rr * C + coff, d[u]);
-                IO<T>::load8(x + rr * C + coff, z[u]);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const long long rr = r + static_cast<long long>(u) * R;
-            if (ok[u]) {
-                if (pre) {
+    for (int i = 0; i < sp.n; ++i) {
+        const int s = i % NS;
+        ring.wait_full(s);
+        const int npk = chunk_rows_of(g, sp.chunk0 + i) * L;
+        const T* ds = reinterpret_cast<const T*>(ring.buf(s, 0));
+        const T* xs = reinterpret_cast<const T*>(ring.buf(s, 1));
+        const T* ps = reinterpret_cast<const T*>(ring.buf(s, k_pre));
+        const T* ys = reinterpret_cast<const T*>(ring.buf(s, k_y));
+        for (int j = 0; j < g.ppt; ++j) {
+            const int q = tid + j * kThreads;
+            if (q < npk) {
+                float d[8], z[8];
+                IO<T>::load8(ds + q * 8, d);
+                IO<T>::load8(xs + q * 8, z);
+                if (has_pre) {
                     float t[8];
-                    IO<T>::load8(pre + rr * C + coff, t);
+                    IO<T>::load8(ps + q * 8, t);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) z[u][k] += t[k];
+                    for (int k = 0; k < 8; ++k) z[k] += t[k];
                 }
                 if (relu) {
                     float o[8];
-                    IO<T>::load8(yy + rr * C + coff, o);
+                    IO<T>::load8(ys + q * 8, o);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) d[u][k] = o[k] > 0.f ? d[u][k] : 0.f;
+                    for (int k = 0; k < 8; ++k) d[k] = o[k] > 0.f ? d[k] : 0.f;
                 }
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    a[k] += d[u][k];
-                    a[8 + k] = fmaf(d[u][k], z[u][k] - mean[k], a[8 + k]);
+                    a[k] += d[k];
+                    a[8 + k] = fmaf(d[k], z[k] - mean[k], a[8 + k]);
                 }
             }
         }
-    }
-    float tot = cta_reduce16(a, L, red);
-    if (slab_finish(g, prm.w, slab, strip, red, tot)) {
-        if (tid < n16) {
-            // local parameter gradients (the gradient all-reduce averages them later)
-            const int k = tid / L, ll = tid % L;
-            const int ch = slab * g.slabC + ll * 8 + (k & 7);
-            if (k < 8) prm.dbeta[ch] = tot;
-            else prm.dgamma[ch] = tot * prm.sinvstd[ch];
-            publish(prm.c, prm.use_mc, prm.stats_off, prm.w.ll_local, C, slab * n16 + tid, tot, prm.tag);
+        if (i + NS < sp.n) {
+            ring.release(s);
+            if (tid == 0) {
+                ring.wait_empty(s);
+                issue_chunk<4>(ring, g, csrc, s, sp.chunk0 + i + NS);
+            }
         }
     }
-    __syncthreads();
-    if (tid < n16) {
-        float v;
-        if (!collect(prm.c, prm.stats_off, prm.w.ll_local, C, slab * n16 + tid, prm.tag,
-                     prm.c.timeout_cycles ? prm.c.timeout_cycles : 4000000000ull, v)) {
-            s_fail = 1;
-            if (prm.c.error_flag) atomicExch(prm.c.error_flag, 0xDEAD0002u);
-            v = 0.f;
-        }
-        red[tid] = v;
+    cta_reduce16(a, L, red);
+    {
+        const float* sinv = prm.sinvstd;
+        float* dgamma = prm.dgamma;
+        float* dbeta = prm.dbeta;
+        const int LL = L;
+        // GPU-local totals are also the local parameter gradients (the gradient all-reduce averages them later)
+        exchange(g, prm.w, prm.c, prm.use_mc, prm.stats_off, call_tag(prm.tag, prm.epoch), red, &s_fail, [=](int j, float tot) {
+            const int k = j / LL, ll = j % LL;
+            const int ch = ll * 8 + (k & 7);
+            if (k < 8) dbeta[ch] = tot;
+            else dgamma[ch] = tot * sinv[ch];
+        });
     }
-    __syncthreads();
-    if (s_fail) return;
-    if (tid < g.slabC) {
-        const int cl = tid, ll = cl >> 3, k = cl & 7, ch = slab * g.slabC + cl;
+    {
         const float n = static_cast<float>(g.rows) * static_cast<float>(prm.c.world);
-        const float mean_dy = red[k * L + ll] / n;
-        const float mean_dy_xmu = red[(8 + k) * L + ll] / n;
-        const float invstd = prm.sinvstd[ch];
-        const float A = prm.gamma[ch] * invstd;
-        const float B = -A * invstd * invstd * mean_dy_xmu;
-        s_a[cl] = A;
-        s_b[cl] = B;
-        s_d[cl] = -A * mean_dy - B * prm.smean[ch];
+        for (int ch = tid; ch < C; ch += kThreads) {
+            const int ll = ch >> 3, k = ch & 7;
+            const float mean_dy = red[k * L + ll] / n;
+            const float mean_dy_xmu = red[(8 + k) * L + ll] / n;
+            const float invstd = prm.sinvstd[ch];
+            const float A = prm.gamma[ch] * invstd;
+            const float B = -A * invstd * invstd * mean_dy_xmu;
+            s_a[ch] = A;
+            s_b[ch] = B;
+            s_d[ch] = -A * mean_dy - B * prm.smean[ch];
+        }
     }
     __syncthreads();
 
-    // ---- phase 2: dz = A dy_m + B z + D ; dres = dy_m ----------------------------------------------------
+    // ---- phase 2: dz = A dy_m + B z + D ; dres = dy_m ----------------------------------------------------------
     float A[8], B[8], D[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -471,96 +612,122 @@ __global__ void __launch_bounds__(kThreads) syncbn_bwd_kernel(const __grid_const
         B[k] = s_b[l * 8 + k];
         D[k] = s_d[l * 8 + k];
     }
-    for (long long r = r0 + rl; r < r1; r += 2ll * R) {
-        float d[2][8], z[2][8];
-        bool ok[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const long long rr = r + static_cast<long long>(u) * R;
-            ok[u] = rr < r1;
-            if (ok[u]) {
-                IO<T>::load8(dy + rr * C + coff, d[u]);
-                IO<T>::load8(x + rr * C + coff, z[u]);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const long long rr = r + static_cast<long long>(u) * R;
-            if (ok[u]) {
-                if (pre) {
+    const int nres0 = sp.n > NS ? sp.n - NS : 0;
+    const int nresident = sp.n - nres0;
+    for (int i2 = 0; i2 < sp.n; ++i2) {
+        const bool streamed = i2 >= nresident;
+        const int c = streamed ? nres0 - 1 - (i2 - nresident) : nres0 + i2;
+        const int s = (nres0 + i2) % NS;
+        if (streamed) ring.wait_full(s);
+        const long long chunk = sp.chunk0 + c;
+        const int npk = chunk_rows_of(g, chunk) * L;
+        const T* ds = reinterpret_cast<const T*>(ring.buf(s, 0));
+        const T* xs = reinterpret_cast<const T*>(ring.buf(s, 1));
+        const T* ps = reinterpret_cast<const T*>(ring.buf(s, k_pre));
+        const T* ys = reinterpret_cast<const T*>(ring.buf(s, k_y));
+        const size_t ebase = static_cast<size_t>(chunk) * g.chunk_rows * C;
+        for (int j = 0; j < g.ppt; ++j) {
+            const int q = tid + j * kThreads;
+            if (q < npk) {
+                float d[8], z[8];
+                IO<T>::load8(ds + q * 8, d);
+                IO<T>::load8(xs + q * 8, z);
+                if (has_pre) {
                     float t[8];
-                    IO<T>::load8(pre + rr * C + coff, t);
+                    IO<T>::load8(ps + q * 8, t);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) z[u][k] += t[k];
+                    for (int k = 0; k < 8; ++k) z[k] += t[k];
                 }
                 if (relu) {
                     float o[8];
-                    IO<T>::load8(yy + rr * C + coff, o);
+                    IO<T>::load8(ys + q * 8, o);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) d[u][k] = o[k] > 0.f ? d[u][k] : 0.f;
+                    for (int k = 0; k < 8; ++k) d[k] = o[k] > 0.f ? d[k] : 0.f;
                 }
-                if (dres) IO<T>::store8(dres + rr * C + coff, d[u]);
+                if (gdres) IO<T>::store8(gdres + ebase + static_cast<size_t>(q) * 8, d);
                 float o[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) o[k] = fmaf(A[k], d[u][k], fmaf(B[k], z[u][k], D[k]));
-                IO<T>::store8(dz + rr * C + coff, o);
+                for (int k = 0; k < 8; ++k) o[k] = fmaf(A[k], d[k], fmaf(B[k], z[k], D[k]));
+                IO<T>::store8(gdz + ebase + static_cast<size_t>(q) * 8, o);
+            }
+        }
+        if (i2 < nres0) {
+            ring.release(s);
+            if (tid == 0) {
+                ring.wait_empty(s);
+                issue_chunk<4>(ring, g, csrc, s, sp.chunk0 + (nres0 - 1 - i2));
             }
         }
     }
 }
 
 // ---- host side ------------------------------------------------------------------------------------------
-static int make_geom(int64_t rows, int C, int dtype, int max_ctas, BnGeom& g) {
-    if (rows <= 0 || C <= 0 || (C % 8) != 0) return SOD_EUNSUPPORTED;
-    (void)dtype;
+static int make_geom(int64_t rows, int C, int dtype, int nstream, int chunk_bytes, BnGeom& g) {
+    if (rows <= 0 || C <= 0 || (C % 8) != 0 || C > kMaxC) return SOD_EUNSUPPORTED;
     g.C = C;
     g.rows = rows;
-    g.slabC = C < kSlabMax ? C : kSlabMax;
-    if (C % g.slabC) return SOD_EUNSUPPORTED;
-    g.L = g.slabC / 8;
-    if (g.L & (g.L - 1)) return SOD_EUNSUPPORTED;  // lanes per row must be a power of two (≤32)
-    g.R = kThreads / g.L;
-    g.slabs = C / g.slabC;
-    if (g.slabs > kMaxSlabs) return SOD_EUNSUPPORTED;
-    long long strips = (rows + 4ll * g.R - 1) / (4ll * g.R);  // ≥ ~4 row-iterations per CTA
-    long long cap = max_ctas / g.slabs;
-    if (cap < 1) cap = 1;
+    g.es = (dtype == SOD_F32) ? 4 : 2;
+    g.L = C / 8;
+    if ((g.L & (g.L - 1)) || g.L > 256) return SOD_EUNSUPPORTED;  // lanes per row: power of two ≤ 256
+    while (C * g.es > chunk_bytes) chunk_bytes *= 2;                // a chunk holds at least one row
+    g.chunk_bytes = chunk_bytes;
+    g.chunk_rows = chunk_bytes / (C * g.es);
+    const int ppc = chunk_bytes / (8 * g.es);                       // packets per chunk
+    g.ppt = (ppc + kThreads - 1) / kThreads;
+    g.nstream = nstream;
+    const DevInfo& dv = dev_info();
+    const long long budget = static_cast<long long>(dv.max_smem_optin) - kSmemFixed - 1024;
+    int nstage = static_cast<int>(budget / (static_cast<long long>(nstream) * chunk_bytes));
+    if (nstage > kMaxStages) nstage = kMaxStages;
+    if (nstage < 2) return SOD_EUNSUPPORTED;
+    g.nstage = nstage;
+    g.total_chunks = (rows + g.chunk_rows - 1) / g.chunk_rows;
+    long long strips = g.total_chunks;
+    long long cap = dv.sm_count < kMaxGrid ? dv.sm_count : kMaxGrid;
+    // hop-1 packets cost strips*2C*8 bytes of traffic: keep that well below the tensor itself
+    const long long tensor_bytes = rows * C * g.es;
+    long long by_traffic = tensor_bytes / (4ll * 2 * C * 8);
+    if (by_traffic < 1) by_traffic = 1;
+    if (cap > by_traffic) cap = by_traffic;
     if (strips > cap) strips = cap;
-    if (strips < 1) strips = 1;
-    g.rows_per_strip = (rows + strips - 1) / strips;
-    g.strips = static_cast<int>((rows + g.rows_per_strip - 1) / g.rows_per_strip);
+    g.chunks_per_strip = static_cast<int>((g.total_chunks + strips - 1) / strips);
+    g.strips = static_cast<int>((g.total_chunks + g.chunks_per_strip - 1) / g.chunks_per_strip);
     return SOD_OK;
 }
 
-template <typename K>
-static int max_resident(K kern) {
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
-    return per_sm * dev_info().sm_count;
+static size_t bn_ws_layout(int C, BnWork* w, void* base) {
+    size_t off = 0;
+    if (w) w->ll_local = reinterpret_cast<uint2*>(static_cast<char*>(base) + off);
+    off += static_cast<size_t>(2) * kMaxC * sizeof(uint2);
+    if (w) w->partials = reinterpret_cast<uint2*>(static_cast<char*>(base) + off);
+    off += static_cast<size_t>(kMaxGrid) * 2 * C * sizeof(uint2);
+    return off;
 }
 
-static size_t bn_ws_layout(const BnGeom* g, int C, BnWork* w, void* base) {
-    // [counters 256 B][ll_local 2C*8][partials]
-    size_t off = 0;
-    if (w) w->counters = reinterpret_cast<unsigned*>(static_cast<char*>(base) + off);
-    off += kMaxSlabs * sizeof(unsigned);
-    if (w) w->ll_local = reinterpret_cast<uint2*>(static_cast<char*>(base) + off);
-    off += static_cast<size_t>(2) * C * sizeof(uint2);
-    if (w) w->partials = reinterpret_cast<float*>(static_cast<char*>(base) + off);
-    if (g) off += static_cast<size_t>(g->slabs) * g->strips * 16 * g->L * sizeof(float);
-    return off;
+template <typename K>
+static int launch_bn(K kern, const void* prm, const BnGeom& g, int nstream, cudaStream_t stream) {
+    const size_t smem = kSmemFixed + static_cast<size_t>(g.nstage) * nstream * g.chunk_bytes;
+    static thread_local const void* configured[8] = {nullptr};   // per kernel instantiation, once per thread
+    cudaError_t e;
+    bool done = false;
+    for (const void* c : configured) done |= (c == reinterpret_cast<const void*>(kern));
+    if (!done) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_info().max_smem_optin - 1024);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        for (auto& c : configured)
+            if (c == nullptr) { c = reinterpret_cast<const void*>(kern); break; }
+    }
+    void* args[] = {const_cast<void*>(prm)};
+    e = cudaLaunchKernel(reinterpret_cast<const void*>(kern), dim3(g.strips), dim3(kThreads), args, smem, stream);
+    return static_cast<int>(e);
 }
 
 }  // namespace
 }  // namespace sod
 
 extern "C" size_t sod_syncbn_workspace_bytes(int64_t rows, int channels) {
-    using namespace sod;
     (void)rows;
-    // upper bound independent of the device: every CTA of a 2-CTA/SM grid on ≤ 256 SMs writes 2*slabC floats
-    const size_t slabC = channels < kSlabMax ? channels : kSlabMax;
-    return kMaxSlabs * sizeof(unsigned) + static_cast<size_t>(2) * channels * sizeof(uint2) +
-           static_cast<size_t>(1024) * 2 * slabC * sizeof(float);
+    return sod::bn_ws_layout(channels > 0 ? channels : sod::kMaxC, nullptr, nullptr);
 }
 
 extern "C" size_t sod_syncbn_exchange_bytes(int channels) {
@@ -571,7 +738,8 @@ extern "C" int sod_syncbn_fwd(const void* x, const void* pre_add, const void* re
                               const float* gamma, const float* beta, float* running_mean, float* running_var,
                               float* save_mean, float* save_invstd, int64_t rows, int channels, float momentum,
                               float eps, int relu, int training, const sod_comm* comm, uint64_t stats_off,
-                              uint32_t seq, void* workspace, size_t workspace_bytes, int flags, void* stream) {
+                              uint32_t seq, const uint32_t* epoch, int64_t* num_batches_tracked, void* workspace,
+                              size_t workspace_bytes, int flags, void* stream) {
     using namespace sod;
     SOD_CHECK_ARG(x && y && gamma && beta && workspace, SOD_EINVAL);
     SOD_CHECK_ARG(training ? (save_mean && save_invstd) : (running_mean && running_var), SOD_EINVAL);
@@ -587,27 +755,26 @@ extern "C" int sod_syncbn_fwd(const void* x, const void* pre_add, const void* re
         SOD_CHECK_ARG(stats_off >= sod_comm_flag_bytes() &&
                           stats_off + sod_syncbn_exchange_bytes(channels) <= comm->arena_bytes, SOD_ECOMM);
     }
-    return SOD_DISPATCH_DTYPE(dtype, T, [&]() -> int {
-        auto kern = syncbn_fwd_kernel<T>;
-        rc = make_geom(rows, channels, dtype, max_resident(kern), p.g);
-        if (rc != SOD_OK) return rc;
-        if (bn_ws_layout(&p.g, channels, &p.w, workspace) > workspace_bytes) return SOD_EWORKSPACE;
-        p.x = x; p.pre = pre_add; p.res = residual; p.y = y;
-        p.gamma = gamma; p.beta = beta; p.rmean = running_mean; p.rvar = running_var;
-        p.smean = save_mean; p.sinvstd = save_invstd;
-        p.momentum = momentum; p.eps = eps; p.relu = relu; p.training = training;
-        p.stats_off = stats_off; p.tag = seq;
-        p.use_mc = (p.c.mc != 0) && !(flags & SOD_ALGO_NO_MULTIMEM);
-        kern<<<p.g.slabs * p.g.strips, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
-        return static_cast<int>(cudaGetLastError());
-    });
+    const int nstream = pre_add ? 2 : 1;
+    rc = make_geom(rows, channels, dtype, nstream, 16384, p.g);
+    if (rc != SOD_OK) return rc;
+    if (bn_ws_layout(channels, &p.w, workspace) > workspace_bytes) return SOD_EWORKSPACE;
+    p.x = x; p.pre = pre_add; p.res = residual; p.y = y;
+    p.gamma = gamma; p.beta = beta; p.rmean = running_mean; p.rvar = running_var;
+    p.smean = save_mean; p.sinvstd = save_invstd;
+    p.nbt = training ? reinterpret_cast<long long*>(num_batches_tracked) : nullptr;
+    p.momentum = momentum; p.eps = eps; p.relu = relu; p.training = training;
+    p.stats_off = stats_off; p.tag = seq; p.epoch = epoch;
+    p.use_mc = (p.c.mc != 0) && !(flags & SOD_ALGO_NO_MULTIMEM);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    return SOD_DISPATCH_DTYPE(dtype, T, [&]() -> int { return launch_bn(syncbn_fwd_kernel<T>, &p, p.g, nstream, s); });
 }
 
 extern "C" int sod_syncbn_bwd(const void* dy, const void* x, const void* pre_add, const void* y, void* dz, void* dres,
                               int dtype, const float* gamma, const float* save_mean, const float* save_invstd,
                               float* dgamma, float* dbeta, int64_t rows, int channels, int relu, const sod_comm* comm,
-                              uint64_t stats_off, uint32_t seq, void* workspace, size_t workspace_bytes, int flags,
-                              void* stream) {
+                              uint64_t stats_off, uint32_t seq, const uint32_t* epoch, void* workspace,
+                              size_t workspace_bytes, int flags, void* stream) {
     using namespace sod;
     SOD_CHECK_ARG(dy && x && dz && gamma && save_mean && save_invstd && dgamma && dbeta && workspace, SOD_EINVAL);
     SOD_CHECK_ARG(!relu || y, SOD_EINVAL);
@@ -622,16 +789,14 @@ extern "C" int sod_syncbn_bwd(const void* dy, const void* x, const void* pre_add
         SOD_CHECK_ARG(stats_off >= sod_comm_flag_bytes() &&
                           stats_off + sod_syncbn_exchange_bytes(channels) <= comm->arena_bytes, SOD_ECOMM);
     }
-    return SOD_DISPATCH_DTYPE(dtype, T, [&]() -> int {
-        auto kern = syncbn_bwd_kernel<T>;
-        rc = make_geom(rows, channels, dtype, max_resident(kern), p.g);
-        if (rc != SOD_OK) return rc;
-        if (bn_ws_layout(&p.g, channels, &p.w, workspace) > workspace_bytes) return SOD_EWORKSPACE;
-        p.dy = dy; p.x = x; p.pre = pre_add; p.y = y; p.dz = dz; p.dres = dres;
-        p.gamma = gamma; p.smean = save_mean; p.sinvstd = save_invstd; p.dgamma = dgamma; p.dbeta = dbeta;
-        p.relu = relu; p.stats_off = stats_off; p.tag = seq;
-        p.use_mc = (p.c.mc != 0) && !(flags & SOD_ALGO_NO_MULTIMEM);
-        kern<<<p.g.slabs * p.g.strips, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
-        return static_cast<int>(cudaGetLastError());
-    });
+    const int nstream = 2 + (pre_add ? 1 : 0) + (relu ? 1 : 0);
+    rc = make_geom(rows, channels, dtype, nstream, 8192, p.g);
+    if (rc != SOD_OK) return rc;
+    if (bn_ws_layout(channels, &p.w, workspace) > workspace_bytes) return SOD_EWORKSPACE;
+    p.dy = dy; p.x = x; p.pre = pre_add; p.y = relu ? y : nullptr; p.dz = dz; p.dres = dres;
+    p.gamma = gamma; p.smean = save_mean; p.sinvstd = save_invstd; p.dgamma = dgamma; p.dbeta = dbeta;
+    p.relu = relu; p.stats_off = stats_off; p.tag = seq; p.epoch = epoch;
+    p.use_mc = (p.c.mc != 0) && !(flags & SOD_ALGO_NO_MULTIMEM);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    return SOD_DISPATCH_DTYPE(dtype, T, [&]() -> int { return launch_bn(syncbn_bwd_kernel<T>, &p, p.g, nstream, s); });
 }

@@ -9,8 +9,8 @@ from __future__ import annotations
 
 import torch
 
-from . import amp, comm, network
-from .loss import CEL, BCEWithLogitsLoss, get_total_loss
+from . import _lib, amp, comm, network, syncbn
+from .loss import CEL, BCEWithLogitsLoss, _FusedLossFn, get_total_loss
 from .optim import CustomScheduler, make_optimizer
 from .parallel import DistributedDataParallel
 from .syncbn import convert_syncbn_model
@@ -21,7 +21,7 @@ class Trainer:
     def __init__(self, model_name: str = "res50", lr: float = 0.05, momentum: float = 0.9, weight_decay: float = 5e-4,
                  nesterov: bool = False, optim: str = "f3_trick", reduction: str = "mean", use_aux_loss: bool = True,
                  dtype: torch.dtype = torch.bfloat16, channels_last: bool = True, seed: int = 0,
-                 device: torch.device | None = None, report_items: bool = True):
+                 device: torch.device | None = None, report_items: bool = True, use_graph: bool = False):
         if not torch.cuda.is_available():
             raise RuntimeError("the B200 engine needs a CUDA device")
         self.device = device or torch.device("cuda", torch.cuda.current_device())
@@ -47,6 +47,10 @@ class Trainer:
         self.model.train()
         self._pinned_loss = torch.zeros(1, dtype=torch.float32).pin_memory()
         self._loss_event: torch.cuda.Event | None = None
+        # CUDA-graph replay of the whole iteration: one cudaGraphLaunch instead of ~1500 launches
+        self.use_graph = use_graph and not amp._cfg["dynamic"]
+        self._graph = None
+        self._graph_key = None
 
     @property
     def module(self):
@@ -56,20 +60,17 @@ class Trainer:
         return CustomScheduler(self.optimizer, total_num, lr_type, dict(lr_decay=lr_decay, warmup_epoch=warmup_epoch))
 
     # ----------------------------------------------------------------------------------------------
-    def forward_backward_update(self, x: torch.Tensor, m: torch.Tensor):
-        """device tensors in, device loss out; no host synchronisation"""
+    def _iteration(self, x: torch.Tensor, m: torch.Tensor, report: bool):
         if self.channels_last:
             x = x.contiguous(memory_format=torch.channels_last)
         preds = self.model(x)                                              # train.py:293
-        fused = len(self.loss_funcs) == 2
-        if fused and not self.report_items:
-            from .loss import _FusedLossFn
+        unit = not amp._cfg["dynamic"]
+        if len(self.loss_funcs) == 2 and not report:
             holder: list = []
-            unit = not amp._cfg["dynamic"]
             loss = _FusedLossFn.apply(preds, m, self.loss_funcs[0].reduction, 1.0, 1.0, 1e-6, unit, 0, holder)
-            items = holder[0]
+            items = holder[0]                                              # device scalars [bce, cel, total, ...]
         else:
-            loss, items = get_total_loss(preds, m, self.loss_funcs, unit_upstream=not amp._cfg["dynamic"])  # train.py:295
+            loss, items = get_total_loss(preds, m, self.loss_funcs, unit_upstream=unit)   # train.py:295
         self.optimizer.zero_grad()                                         # train.py:297
         if self.use_amp:
             with amp.scale_loss(loss, self.optimizer) as scaled:           # train.py:299
@@ -80,6 +81,49 @@ class Trainer:
         reduced = comm.allreduce_tensor(loss.detach()) if self.world > 1 else loss.detach()   # train.py:306
         return reduced, items, preds
 
+    def _capture(self, x: torch.Tensor, m: torch.Tensor):
+        """warm up eagerly on a side stream, then record one whole iteration into a CUDA graph"""
+        self._static_x, self._static_m = x.clone(), m.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._iteration(self._static_x, self._static_m, report=False)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        launches0 = _lib.launches
+        syncbn.begin_iteration(self.device, graph=True)
+        try:
+            with torch.cuda.graph(graph):
+                red, items, preds = self._iteration(self._static_x, self._static_m, report=False)
+                syncbn.end_iteration(self.device)
+                self._static_out = (red, items, preds)
+        finally:
+            syncbn.begin_iteration(self.device, graph=False)
+        self._graph = graph
+        self._graph_launches = _lib.launches - launches0      # hand-written kernels recorded in the graph
+        self._graph_key = (tuple(x.shape), tuple(m.shape), x.dtype, tuple(g["lr"] for g in self.optimizer.param_groups))
+
+    def forward_backward_update(self, x: torch.Tensor, m: torch.Tensor, report: bool | None = None):
+        """device tensors in, device loss out; no host synchronisation unless report strings are requested"""
+        report = self.report_items if report is None else report
+        if not self.use_graph:
+            return self._iteration(x, m, report)
+        key = (tuple(x.shape), tuple(m.shape), x.dtype, tuple(g["lr"] for g in self.optimizer.param_groups))
+        if self._graph is None or key != self._graph_key:     # first call, new multi-scale size, or the lr moved
+            self._graph = None
+            self._capture(x, m)
+        self._static_x.copy_(x, non_blocking=True)
+        self._static_m.copy_(m, non_blocking=True)
+        self._graph.replay()
+        self.optimizer.steps += 1
+        _lib.count_launch(self._graph_launches)
+        red, items, preds = self._static_out
+        if report:
+            items = [f"{v:.5f}" for v in items[:2].tolist()]
+        return red, items, preds
+
     def step(self, x: torch.Tensor, m: torch.Tensor) -> dict:
         """the loop body with the reference's reporting: returns python floats / strings (host sync)."""
         reduced, items, preds = self.forward_backward_update(x, m)
@@ -89,9 +133,18 @@ class Trainer:
     def step_from_host(self, x_pinned: torch.Tensor, m_pinned: torch.Tensor):
         """end-to-end form: pinned host batch → device (train.py:291-292) → iteration → loss back to pinned host
         memory.  The D2H read is asynchronous; `last_loss()` waits for it."""
-        x = x_pinned.to(self.device, non_blocking=True)
-        m = m_pinned.to(self.device, non_blocking=True)
-        reduced, _, _ = self.forward_backward_update(x, m)
+        if self.use_graph and self._graph is not None and tuple(x_pinned.shape) == self._graph_key[0]:
+            # H2D straight into the graph's static inputs
+            self._static_x.copy_(x_pinned, non_blocking=True)
+            self._static_m.copy_(m_pinned, non_blocking=True)
+            self._graph.replay()
+            self.optimizer.steps += 1
+            _lib.count_launch(self._graph_launches)
+            reduced = self._static_out[0]
+        else:
+            x = x_pinned.to(self.device, non_blocking=True)
+            m = m_pinned.to(self.device, non_blocking=True)
+            reduced, _, _ = self.forward_backward_update(x, m, report=False)
         self._pinned_loss.copy_(reduced.reshape(1), non_blocking=True)
         self._loss_event = torch.cuda.Event()
         self._loss_event.record()

@@ -163,8 +163,7 @@ class FusedSGD(Optimizer):
         else:
             a = f.arena
             rc = _lib.lib().sod_allreduce_sgd(a.ref, f.grad_off, f.param_off, f.mom.data_ptr(), f.numel, segs, n,
-                                              float(self.inv_scale), finf, a.next_seq(0), _lib.SOD_SGD_ZERO_GRAD,
-                                              _lib.stream_ptr())
+                                              float(self.inv_scale), finf, _lib.SOD_SGD_ZERO_GRAD, _lib.stream_ptr())
             _lib.check(rc, "sod_allreduce_sgd")
         _lib.count_launch()
         self._grads_clean = True

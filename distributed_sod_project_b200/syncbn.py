@@ -22,28 +22,51 @@ import torch.nn as nn
 from . import _lib, comm
 
 _state: dict = {}
+FORCE_LOCAL = False         # bench.py roofline replay: run single-rank (no exchange) even inside a process group
 TRACE: list | None = None   # bench.py: when a list, every forward call appends (n, c, h, w, has_pre, has_res, relu)
 
 
 def _dev_state(device: torch.device) -> dict:
     st = _state.get(device.index)
     if st is None:
-        nbytes = int(_lib.lib().sod_syncbn_workspace_bytes(1, 4096))
-        st = {"ws": torch.zeros(nbytes, dtype=torch.uint8, device=device), "seq": 0}
+        nbytes = int(_lib.lib().sod_syncbn_workspace_bytes(1, 2048))
+        st = {"ws": torch.zeros(nbytes, dtype=torch.uint8, device=device), "seq": 0,
+              "epoch": torch.zeros(1, dtype=torch.int32, device=device), "graph": False, "idx": 0}
         _state[device.index] = st
     return st
 
 
-def _next_call(device: torch.device):
-    """(workspace, seq, comm_ref, stats_off): one global sequence over ALL BN launches of this process —
-    the packet tags must be unique across forward and backward calls that share slots."""
+def begin_iteration(device: torch.device, graph: bool) -> None:
+    """graph=True: tags of the coming BN calls are (device epoch, call index) so that the captured iteration can
+    be replayed; the captured code must end with `end_iteration` (epoch += 1 on the device)."""
     st = _dev_state(device)
-    st["seq"] = (st["seq"] + 1) & 0xFFFFFFFF or 1
-    seq = st["seq"]
-    arena = comm.small_arena()
+    st["graph"], st["idx"] = graph, 0
+
+
+def end_iteration(device: torch.device) -> None:
+    st = _dev_state(device)
+    if st["graph"]:
+        st["epoch"].add_(1)          # captured: one tiny kernel per replay
+        st["graph"] = False
+
+
+def _next_call(device: torch.device):
+    """(workspace, seq, epoch_ptr, comm_ref, stats_off).  Eager: one global sequence over ALL BN launches of this
+    process (tags must be unique across forward and backward calls sharing slots).  Graph capture: call index
+    within the iteration + the device-side epoch."""
+    st = _dev_state(device)
+    if st["graph"]:
+        st["idx"] += 1
+        if st["idx"] > 1023:
+            raise _lib.SodError("more than 1023 SyncBN launches in one captured iteration")
+        seq, epoch = st["idx"], st["epoch"].data_ptr()
+    else:
+        st["seq"] = (st["seq"] + 1) & 0x7FFFFFFF or 1
+        seq, epoch = st["seq"], None
+    arena = None if FORCE_LOCAL else comm.small_arena()
     if arena is None:
-        return st["ws"], seq, None, 0
-    return st["ws"], seq, arena.ref, arena.bn_slots[seq % len(arena.bn_slots)]
+        return st["ws"], seq, epoch, None, 0
+    return st["ws"], seq, epoch, arena.ref, arena.bn_slots[seq % len(arena.bn_slots)]
 
 
 def _as_rows(t: torch.Tensor) -> torch.Tensor:
@@ -55,7 +78,7 @@ def _as_rows(t: torch.Tensor) -> torch.Tensor:
 
 class _SyncBNFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, pre_add, residual, weight, bias, running_mean, running_var, momentum, eps, relu, training):
+    def forward(ctx, x, pre_add, residual, weight, bias, running_mean, running_var, nbt, momentum, eps, relu, training):
         x = _as_rows(x)
         pre = _as_rows(pre_add).to(x.dtype) if pre_add is not None else None
         res = _as_rows(residual).to(x.dtype) if residual is not None else None
@@ -67,14 +90,15 @@ class _SyncBNFn(torch.autograd.Function):
         dev = x.device
         mean = torch.empty(c, dtype=torch.float32, device=dev)
         invstd = torch.empty(c, dtype=torch.float32, device=dev)
-        ws, seq, cref, soff = _next_call(dev)
+        ws, seq, epoch, cref, soff = _next_call(dev)
         rc = _lib.lib().sod_syncbn_fwd(
             x.data_ptr(), pre.data_ptr() if pre is not None else None, res.data_ptr() if res is not None else None,
             y.data_ptr(), _lib.dtype_code(x.dtype), weight.data_ptr(), bias.data_ptr(),
             running_mean.data_ptr() if running_mean is not None else None,
             running_var.data_ptr() if running_var is not None else None,
             mean.data_ptr(), invstd.data_ptr(), rows, c, float(momentum), float(eps), int(relu), int(training),
-            cref, soff, seq, ws.data_ptr(), ws.numel(), 0, _lib.stream_ptr())
+            cref, soff, seq, epoch, nbt.data_ptr() if nbt is not None else None, ws.data_ptr(), ws.numel(), 0,
+            _lib.stream_ptr())
         _lib.check(rc, "sod_syncbn_fwd")
         _lib.count_launch()
         ctx.relu, ctx.has_pre, ctx.has_res = bool(relu), pre is not None, res is not None
@@ -86,7 +110,7 @@ class _SyncBNFn(torch.autograd.Function):
         x, pre, y, weight, mean, invstd = ctx.saved_tensors
         dz, dres, dgamma, dbeta = raw_backward(_as_rows(dy).to(x.dtype), x, pre, y, weight, mean, invstd, ctx.relu, ctx.has_res)
         return (dz, dz if ctx.has_pre else None, dres, dgamma.to(weight.dtype), dbeta.to(weight.dtype),
-                None, None, None, None, None, None)
+                None, None, None, None, None, None, None)
 
 
 def raw_backward(dy, x, pre, y, weight, mean, invstd, relu: bool, want_dres: bool):
@@ -96,12 +120,12 @@ def raw_backward(dy, x, pre, y, weight, mean, invstd, relu: bool, want_dres: boo
     dres = torch.empty_like(x) if want_dres else None
     dgamma = torch.empty(c, dtype=torch.float32, device=x.device)
     dbeta = torch.empty(c, dtype=torch.float32, device=x.device)
-    ws, seq, cref, soff = _next_call(x.device)
+    ws, seq, epoch, cref, soff = _next_call(x.device)
     rc = _lib.lib().sod_syncbn_bwd(
         dy.data_ptr(), x.data_ptr(), pre.data_ptr() if pre is not None else None,
         y.data_ptr() if (relu and y is not None) else None, dz.data_ptr(), dres.data_ptr() if dres is not None else None,
         _lib.dtype_code(x.dtype), weight.data_ptr(), mean.data_ptr(), invstd.data_ptr(), dgamma.data_ptr(),
-        dbeta.data_ptr(), n * h * w, c, int(relu), cref, soff, seq, ws.data_ptr(), ws.numel(), 0, _lib.stream_ptr())
+        dbeta.data_ptr(), n * h * w, c, int(relu), cref, soff, seq, epoch, ws.data_ptr(), ws.numel(), 0, _lib.stream_ptr())
     _lib.check(rc, "sod_syncbn_bwd")
     _lib.count_launch()
     return dz, dres, dgamma, dbeta
@@ -120,17 +144,17 @@ class SyncBatchNorm(nn.BatchNorm2d):
         if x.shape[1] != self.num_features:
             raise ValueError(f"expected {self.num_features} channels, got {x.shape[1]}")
         training = self.training or self.running_mean is None
-        momentum = 0.0
+        momentum, nbt = 0.0, None
         if training and self.track_running_stats:
-            if self.num_batches_tracked is not None:
-                self.num_batches_tracked.add_(1)
-            # momentum=None means cumulative average in torch; the reference never uses it
-            momentum = self.momentum if self.momentum is not None else 1.0 / float(self.num_batches_tracked)
+            nbt = self.num_batches_tracked          # incremented inside the kernel (saves 84 tiny launches / iteration)
+            if self.momentum is None:
+                raise _lib.SodError("momentum=None (cumulative moving average) is not on the reference's hot path")
+            momentum = self.momentum
         rm = self.running_mean if self.track_running_stats else None
         rv = self.running_var if self.track_running_stats else None
         weight = self.weight if self.affine else torch.ones(self.num_features, device=x.device)
         bias = self.bias if self.affine else torch.zeros(self.num_features, device=x.device)
-        return _SyncBNFn.apply(x, pre_add, residual, weight, bias, rm, rv, momentum, self.eps, relu, training)
+        return _SyncBNFn.apply(x, pre_add, residual, weight, bias, rm, rv, nbt, momentum, self.eps, relu, training)
 
 
 def convert_syncbn_model(module: nn.Module, process_group=None, channel_last: bool = True) -> nn.Module:

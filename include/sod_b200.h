@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SOD_ABI_VERSION 1
+#define SOD_ABI_VERSION 2
 #define SOD_MAX_WORLD 8
 #define SOD_MAX_SEGMENTS 16
 #define SOD_COMM_MAX_BLOCKS 1024   /* flag rows per channel */
@@ -78,6 +78,9 @@ typedef struct {
     uint64_t arena_bytes;
     uint32_t* error_flag;   /* device word in local memory; set non-zero on a barrier timeout */
     uint64_t timeout_cycles;/* bounded spin; 0 = default (~20 s) */
+    uint32_t* block_seq;    /* device array [SOD_COMM_CHANNELS*SOD_COMM_MAX_BLOCKS] in LOCAL memory, zeroed once:
+                               per-block barrier sequence numbers, advanced by the kernels themselves, so the
+                               collectives carry no host-side sequence number and replay inside CUDA graphs */
 } sod_comm;
 size_t sod_comm_flag_bytes(void);
 
@@ -109,25 +112,30 @@ int sod_sgd_momentum(float* param, float* mom, float* grad, int64_t n, const sod
                      int nseg, float inv_scale, const uint32_t* found_inf, int flags, void* stream);
 int sod_allreduce_sgd(const sod_comm* comm, uint64_t grad_off, uint64_t param_off, float* mom, int64_t n,
                       const sod_sgd_segment* segs, int nseg, float inv_scale, const uint32_t* found_inf,
-                      uint32_t seq, int flags, void* stream);
+                      int flags, void* stream);
 /* *found_inf |= any(!isfinite(grad)) — the amp overflow check (train.py:299), one read of grad */
 int sod_grad_nonfinite(const float* grad, int64_t n, uint32_t* found_inf, void* stream);
 
 /* plain in-place SUM all-reduce of fp32 data at arena offset `off` (BASELINE config 5 sweep; also the
  * scalar loss mean of utils/tensor_ops.py:60-64 with scale = 1/W).  algo: 0 auto, 1 one-shot, 2 two-shot */
-int sod_allreduce_f32(const sod_comm* comm, uint64_t off, int64_t n, float scale, int algo, uint32_t seq,
-                      int flags, void* stream);
+int sod_allreduce_f32(const sod_comm* comm, uint64_t off, int64_t n, float scale, int algo, int flags,
+                      void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (2) SyncBatchNorm, statistics exchange fused with normalize/affine (+ optional pre-add, residual, ReLU).
  * Replaces: apex convert_syncbn_model/SyncBatchNorm forward+backward (train.py:180) — local Welford +
  *           2 all_gathers + elementwise forward; reduce + 2 all_reduces + elementwise backward.
- * Data layout: channels-last matrices [M = N*H*W rows, C channels] (x_dtype ∈ bf16/f16/f32; C % 8 == 0
- * for 16-bit, C % 4 == 0 for f32), fp32 gamma/beta/running stats/saved stats.
+ * Data layout: channels-last matrices [M = N*H*W rows, C channels] (dtype ∈ bf16/f16/f32; C a power-of-two
+ * multiple of 8, C ≤ 2048), fp32 gamma/beta/running stats/saved stats.
  *   z = x (+ pre_add);  mean/var over M*world rows;  y = relu?((z-mean)*invstd*gamma + beta (+ residual))
  * training=0: uses running stats, no exchange.  comm may be NULL (world 1).
- * stats_off: arena offset of the exchange slots (sod_syncbn_exchange_bytes(C) per layer call; the host
- * rotates ≥2 slots); seq: per-channel sequence number, same on all ranks, strictly increasing.
+ * stats_off: arena offset of the exchange slot for this call (sod_syncbn_exchange_bytes(C) bytes; the host
+ * rotates ≥2 slots); seq/epoch: the packet tag — it must be unique among all syncbn calls (forward AND
+ * backward) that share a workspace / slot and identical on all ranks for the same call.  epoch == NULL: tag =
+ * seq (31 bits; one global host call counter does it).  epoch != NULL (CUDA-graph replay): tag =
+ * 2^31 | (*epoch << 10) | (seq & 1023), with seq the call index inside the captured iteration and *epoch a
+ * device counter the captured iteration increments once.
+ * workspace: sod_syncbn_workspace_bytes(rows, C) bytes, zero-filled once, then owned by the library.
  * ------------------------------------------------------------------------------------------------ */
 size_t sod_syncbn_workspace_bytes(int64_t rows, int channels);
 size_t sod_syncbn_exchange_bytes(int channels);
@@ -135,14 +143,15 @@ int sod_syncbn_fwd(const void* x, const void* pre_add, const void* residual, voi
                    const float* gamma, const float* beta, float* running_mean, float* running_var,
                    float* save_mean, float* save_invstd, int64_t rows, int channels, float momentum,
                    float eps, int relu, int training, const sod_comm* comm, uint64_t stats_off, uint32_t seq,
-                   void* workspace, size_t workspace_bytes, int flags, void* stream);
+                   const uint32_t* epoch, int64_t* num_batches_tracked /* += 1 when training; may be NULL */, void* workspace,
+                   size_t workspace_bytes, int flags, void* stream);
 /* dz = d/d(x) = d/d(pre_add); dres = relu-masked dy (written only if non-NULL; may alias nothing);
  * dgamma/dbeta: LOCAL sums (the gradient all-reduce averages them with every other parameter). */
 int sod_syncbn_bwd(const void* dy, const void* x, const void* pre_add, const void* y, void* dz, void* dres,
                    int dtype, const float* gamma, const float* save_mean, const float* save_invstd,
                    float* dgamma, float* dbeta, int64_t rows, int channels, int relu, const sod_comm* comm,
-                   uint64_t stats_off, uint32_t seq, void* workspace, size_t workspace_bytes, int flags,
-                   void* stream);
+                   uint64_t stats_off, uint32_t seq, const uint32_t* epoch, void* workspace, size_t workspace_bytes,
+                   int flags, void* stream);
 
 #ifdef __cplusplus
 }

@@ -28,13 +28,14 @@ def test_fp32_trajectory_vs_reference(golden, tag, model):
         # deepest BN) are an ill-conditioned edge case whose later iterations amplify fp32 reassociation noise —
         # the oracle itself moves by 3e-3 at iteration 1 between a 1-process and a 2-process run
         well = tag.endswith("s128")
-        assert out["loss"] == pytest.approx(ref, rel=1e-3 if (well or it == 0) else 3e-2), f"iter {it}"
+        assert out["loss"] == pytest.approx(ref, rel=(1e-3 if it < 2 else 5e-3) if (well or it == 0) else 3e-2), f"iter {it}: got {out['loss']} want {ref}"
         if f"logits{it}" in g.files:
             ref_l = g[f"logits{it}"]
             got = out["preds"].float().cpu().numpy()
             assert np.abs(got - ref_l).max() / np.abs(ref_l).max() < 1e-3
         if it == 0:
-            assert out["items"] == list(g["items0"][0])
+            # report strings are "%.5f" of fp32 values: allow the last printed digit to differ
+            assert np.allclose([float(v) for v in out["items"]], [float(v) for v in g["items0"][0]], atol=2.1e-5)
             # post-step parameters: compare the UPDATE (p1 - p0) — p0 is the seeded init, identical by construction
             from distributed_sod_project_b200 import network
             from distributed_sod_project_b200.utils import init_seed
@@ -66,3 +67,23 @@ def test_bf16_first_step_within_tolerance(golden):
     assert out["loss"] == pytest.approx(float(g["loss0"][0]), rel=5e-3)   # bf16 activations: 2^-8 per op, averaged
     out2 = tr.step(*[t.cuda() for t in synth_batch(2234, 4, 320)])
     assert np.isfinite(out2["loss"])
+
+
+def test_cuda_graph_replay_matches_eager(golden):
+    """the captured iteration (device-epoch packet tags, baked launch parameters) replays to the same trajectory"""
+    from distributed_sod_project_b200.synthetic import synth_batch
+    g = golden("step_res50_w1_s128.npz")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    losses = {}
+    for mode in (False, True):
+        tr = _trainer("res50", dtype=torch.float32, channels_last=True, use_graph=mode, report_items=False)
+        out = []
+        for it in range(4):
+            x, m = synth_batch(1234 + 1000 * it, 4, 128)
+            red, items, _ = tr.forward_backward_update(x.cuda(), m.cuda())
+            out.append(float(red))
+        losses[mode] = out
+    assert losses[True] == pytest.approx(losses[False], rel=2e-4)
+    assert losses[True][0] == pytest.approx(float(g["loss0"][0]), rel=1e-3)
+    assert losses[True][1] == pytest.approx(float(g["loss1"][0]), rel=1e-3)

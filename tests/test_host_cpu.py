@@ -23,12 +23,12 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(h, name), f"{name} declared in include/sod_b200.h but not exported"
     assert declared == set(_lib.EXPORTS)
     lib = _lib.lib()
-    assert lib.sod_version() == 1
+    assert lib.sod_version() == 2
     assert lib.sod_comm_flag_bytes() == 4 * 1024 * 8 * 4
     assert lib.sod_syncbn_exchange_bytes(64) == 8 * 2 * 64 * 8
     assert b"workspace" in lib.sod_strerror(-3)
     # struct layout agrees with the header (sizes are part of the ABI)
-    assert ctypes.sizeof(_lib.sod_sgd_segment) == 32 and ctypes.sizeof(_lib.sod_comm) == 8 + 64 + 8 + 8 + 8 + 8
+    assert ctypes.sizeof(_lib.sod_sgd_segment) == 32 and ctypes.sizeof(_lib.sod_comm) == 8 + 64 + 8 + 8 + 8 + 8 + 8
 
 
 def test_no_cpu_fallback_in_product_path():
