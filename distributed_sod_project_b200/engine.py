@@ -84,12 +84,23 @@ class Trainer:
     def _capture(self, x: torch.Tensor, m: torch.Tensor):
         """warm up eagerly on a side stream, then record one whole iteration into a CUDA graph"""
         self._static_x, self._static_m = x.clone(), m.clone()
+        # the warm-up iterations (allocator, cuDNN autotune, autograd thread) must not move the training state
+        flat = self.optimizer.flat
+        snap = [flat.param.clone(), flat.mom.clone()] + [b.clone() for b in self.module.buffers()]
+        steps, stepped = self.optimizer.steps, self.optimizer._stepped
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(2):
                 self._iteration(self._static_x, self._static_m, report=False)
         torch.cuda.current_stream().wait_stream(side)
+        with torch.no_grad():
+            flat.param.copy_(snap[0]); flat.mom.copy_(snap[1])
+            for b, old in zip(self.module.buffers(), snap[2:]):
+                b.copy_(old)
+        self.optimizer.steps, self.optimizer._stepped = steps, stepped
+        if self.world > 1:
+            torch.distributed.barrier()
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         launches0 = _lib.launches

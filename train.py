@@ -1,0 +1,160 @@
+#!/usr/bin/env python
+"""Training entry point with the reference's command line and configuration surface.
+
+    python train.py [-n NODES] [-ng GPUS_PER_NODE] [--ip IP] [-p PORT]          (reference train.py:48-60)
+
+Same process model as the reference (`torch.multiprocessing.spawn`, one process per GPU, env:// rendezvous,
+train.py:84-101) and the same construction order in `main_worker` (train.py:104-223); the hot path is this repo's
+B200 engine (`distributed_sod_project_b200/engine.py`).  NCCL is still initialised — it bootstraps the symmetric-memory
+rendezvous — but no NCCL collective runs inside an iteration.
+
+Out of scope here: evaluation / metrics (`test`, `_test_process`), TensorBoard / xlsx recorders, dataset
+decoding.  When `user_config["synthetic"]` is set (or the dataset root is absent) batches come from
+`synthetic.synth_batch`, which honours the dataloader's output contract, incl. the multi-scale `size_list` collate.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import random
+import time
+
+import torch
+import torch.distributed as dist
+
+from config import user_config
+from distributed_sod_project_b200 import amp, comm
+from distributed_sod_project_b200.engine import Trainer
+from distributed_sod_project_b200.synthetic import synth_batch
+from distributed_sod_project_b200.utils import (AvgMeter, check_mkdir, construct_exp_name, construct_path_dict, construct_print,
+                                                init_cudnn, write_data_to_file)
+
+parser = argparse.ArgumentParser(prog="main script", description="B200-native engine behind the Distributed-SOD-Project API.",
+                                 allow_abbrev=False)
+parser.version = "1.0.0"
+parser.add_argument("-v", "--version", action="version")
+parser.add_argument("-n", "--nodes", default=1, type=int, metavar="N")
+parser.add_argument("-ng", "--ngpus_per_node", default=2, type=int)
+parser.add_argument("--ip", default="127.0.0.1", type=str)
+parser.add_argument("-p", "--port", default="8888", type=str)
+
+_DTYPES = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}
+
+
+def init_process(ip, port, rank, world_size):
+    os.environ["MASTER_ADDR"] = ip
+    os.environ["MASTER_PORT"] = port
+    dist.init_process_group(backend="nccl", init_method="env://", world_size=world_size, rank=rank,
+                            device_id=torch.device("cuda", rank % torch.cuda.device_count()))
+
+
+class SyntheticLoader:
+    """stands in for `create_loader(ImageFolder(...))` (reference utils/dataset.py:72-156): yields
+    (image[N,3,S,S] f32, mask[N,1,S,S] f32 in [0,1], names); with `size_list` one size per batch, shared by all ranks."""
+
+    def __init__(self, batch_size, iters, in_size, size_list, rank, epoch_seed=0):
+        self.bs, self.iters, self.in_size, self.size_list, self.rank = batch_size, iters, in_size, size_list, rank
+        self.epoch = epoch_seed
+
+    def set_epoch(self, epoch):
+        self.epoch = epoch
+
+    def __len__(self):
+        return self.iters
+
+    def __iter__(self):
+        sizes = random.Random(self.epoch)          # same choice on every rank (shared RNG)
+        for i in range(self.iters):
+            size = sizes.choice(self.size_list) if self.size_list else self.in_size
+            x, m = synth_batch(1234 + self.rank + 1000 * (self.epoch * self.iters + i), self.bs, size)
+            yield x.pin_memory(), m.pin_memory(), [f"synthetic_{self.epoch}_{i}_{k}" for k in range(self.bs)]
+
+
+def main_worker(local_rank, ngpus_per_node, world_size, args, exp_name, path_config):
+    cfg = user_config
+    if local_rank == 0:
+        construct_print(cfg)
+    init_cudnn(benchmark=(cfg["size_list"] is None), deterministic=False)
+    torch.cuda.set_device(local_rank)
+    if cfg["is_distributed"] and world_size > 1:
+        init_process(args.ip, args.port, local_rank, world_size)
+    batch_size_single_gpu = cfg["batch_size"] // ngpus_per_node                        # reference train.py:119
+
+    loader = SyntheticLoader(batch_size_single_gpu, cfg.get("synthetic_iters_per_epoch", 20), cfg["input_size"],
+                             cfg["size_list"], local_rank)
+    total_iter_num = cfg["epoch_num"] * len(loader)
+    if cfg["resume_mode"] == "test":
+        construct_print("evaluation is outside the B200 hot path (SURVEY §2); nothing to do")
+        return
+
+    dtype = _DTYPES[cfg.get("dtype", "bf16")] if cfg["use_amp"] else torch.float32
+    trainer = Trainer(model_name=cfg["model"], lr=cfg["lr"], momentum=cfg["momentum"], weight_decay=cfg["weight_decay"],
+                      nesterov=cfg["nesterov"], optim=cfg["optim"], reduction=cfg["reduction"], use_aux_loss=cfg["use_aux_loss"],
+                      dtype=dtype, channels_last=cfg.get("channels_last", True), report_items=True,
+                      use_graph=cfg.get("cuda_graph", False) and cfg["size_list"] is None)
+    scheduler = trainer.scheduler(total_iter_num if cfg["sche_usebatch"] else cfg["epoch_num"], cfg["lr_type"], cfg["lr_decay"],
+                                  cfg["warmup_epoch"])
+    if local_rank == 0:
+        construct_print(f"optimizer = {trainer.optimizer}")
+        construct_print(f"scheduler = {scheduler}")
+
+    for curr_epoch in range(cfg["epoch_num"]):
+        loader.set_epoch(curr_epoch)
+        if not cfg["sche_usebatch"]:
+            scheduler.step(optimizer=trainer.optimizer, curr_epoch=curr_epoch)
+        trainer.model.train()
+        record = AvgMeter()
+        t0 = time.time()
+        for batch_id, (inputs, masks, names) in enumerate(loader):
+            curr_iter = curr_epoch * len(loader) + batch_id
+            if cfg["sche_usebatch"]:
+                scheduler.step(trainer.optimizer, curr_epoch=curr_iter)
+            inputs = inputs.cuda(non_blocking=True)                                      # train.py:291-292
+            masks = masks.cuda(non_blocking=True)
+            want_log = local_rank == 0 and cfg["print_freq"] > 0 and (curr_iter + 1) % cfg["print_freq"] == 0
+            reduced, items, _ = trainer.forward_backward_update(inputs, masks, report=want_log)
+            if want_log:                                                                 # host sync only when printing
+                loss_val = float(reduced.item())
+                record.update(loss_val, inputs.size(0))
+                lr_str = ",".join(f"{g['lr']:.7f}" for g in trainer.optimizer.param_groups)
+                log = (f"[I:{batch_id}/{len(loader)}/{curr_iter}/{total_iter_num}][E:{curr_epoch}:{cfg['epoch_num']}]>[{exp_name}]"
+                       f"[Lr:{lr_str}][Avg:{record.avg:.5f}|Cur:{loss_val:.5f}|{items}]")
+                print(log)
+                write_data_to_file(log, path_config["tr_log"])
+        torch.cuda.synchronize()
+        if local_rank == 0:
+            n_img = len(loader) * batch_size_single_gpu * max(world_size, 1)
+            construct_print(f"epoch {curr_epoch}: {time.time() - t0:.2f}s, {n_img / (time.time() - t0):.1f} img/s")
+            if (cfg["save_freq"] > 0 and (curr_epoch + 1) % cfg["save_freq"] == 0) or curr_epoch == cfg["epoch_num"] - 1:
+                net_state = trainer.module.state_dict()                                 # utils/pipeline_ops.py:68-78 layout
+                torch.save({"arch": exp_name, "epoch": curr_epoch + 1, "net_state": net_state,
+                            "opti_state": trainer.optimizer.state_dict(),
+                            "amp_state": amp.state_dict() if cfg["use_amp"] else None}, path_config["final_full_net"])
+                torch.save(net_state, path_config["final_state_net"])
+    construct_print("End Training...")
+    if dist.is_initialized():
+        arena = getattr(trainer.model, "arena", None)
+        if arena is not None:
+            arena.check_error()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parser.parse_args()
+    assert torch.cuda.is_available(), "only on GPUs (reference train.py:63)"
+    exp_name = construct_exp_name(user_config)
+    path_config = construct_path_dict(proj_root=user_config["proj_root"], exp_name=exp_name, xlsx_name=user_config["xlsx_name"])
+    check_mkdir(path_config["save"])
+    check_mkdir(path_config["pth"])
+    if user_config["is_distributed"]:
+        construct_print("We will use the distributed training.")
+        world_size = args.ngpus_per_node * args.nodes
+        torch.multiprocessing.spawn(main_worker, nprocs=args.ngpus_per_node,
+                                    args=(args.ngpus_per_node, world_size, args, exp_name, path_config))
+    else:
+        construct_print("We will not use the distributed training.")
+        main_worker(0, 1, 1, args, exp_name, path_config)
+
+
+if __name__ == "__main__":
+    main()
