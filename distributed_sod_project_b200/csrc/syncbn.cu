@@ -31,8 +31,9 @@
 namespace sod {
 namespace {
 
-constexpr int kThreads = 512;
+constexpr int kThreads = 512;             // consumer threads (warps 0..15); every data-layout stride uses this
 constexpr int kWarps = kThreads / 32;
+constexpr int kBlock = kThreads + 32;     // + one producer warp that only issues bulk copies
 constexpr int kMaxC = 2048;
 constexpr int kMaxStages = 16;
 constexpr int kMaxStreams = 4;
@@ -51,7 +52,16 @@ struct BnGeom {
 struct BnWork {
     uint2* partials;   // [strips][2C] packets
     uint2* ll_local;   // [2C] packets, exchange slot when world == 1
+    unsigned long long* stamps;  // [kMaxGrid][4] globaltimer ns when SOD_DEBUG_TIMING is set, else null
 };
+
+__device__ __forceinline__ void stamp(const BnWork& w, int slot) {
+    if (w.stamps != nullptr && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        w.stamps[blockIdx.x * 4 + slot] = t;
+    }
+}
 
 struct BnFwd {
     const void *x, *pre, *res;
@@ -89,6 +99,9 @@ struct BnBwd {
 __device__ __forceinline__ uint32_t call_tag(uint32_t seq, const uint32_t* epoch) {
     return epoch ? (0x80000000u | ((*epoch & 0x1FFFFFu) << 10) | (seq & 1023u)) : (seq & 0x7FFFFFFFu);
 }
+
+// barrier among the 512 consumer threads only (the producer warp never joins it)
+__device__ __forceinline__ void cbar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 // ---- packets -------------------------------------------------------------------------------------------
 __device__ __forceinline__ void st_packet_gpu(uint2* p, float v, uint32_t tag) {
@@ -168,7 +181,7 @@ struct Ring {
         if ((threadIdx.x & 31) == 0)
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[s])) : "memory");
     }
-    // thread 0 only
+    // producer lane only
     __device__ __forceinline__ void wait_empty(int s) {
         mbar_wait(&empty[s], (empty_par >> s) & 1u);
         empty_par ^= 1u << s;
@@ -224,13 +237,13 @@ __device__ __forceinline__ void cta_reduce16(float (&a)[16], int L, float* red /
 #pragma unroll
             for (int k = 0; k < 16; ++k) red[warp * n16 + k * L + lane] = a[k];
         }
-        __syncthreads();
+        cbar();
         float tot = 0.f;
         if (tid < n16) {
 #pragma unroll
             for (int w = 0; w < kWarps; ++w) tot += red[w * n16 + tid];
         }
-        __syncthreads();
+        cbar();
         if (tid < n16) red[tid] = tot;
     } else {
         // L in {64,128,256}: thread tid owns lane l = tid % L; R = kThreads / L threads share it
@@ -238,10 +251,10 @@ __device__ __forceinline__ void cta_reduce16(float (&a)[16], int L, float* red /
         // two rounds of 8 statistics so that the scratch stays within 32 KB: [R][8][L] floats = 16 KB
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-            __syncthreads();
+            cbar();
 #pragma unroll
             for (int k = 0; k < 8; ++k) red[4096 + (r * 8 + k) * L + l] = a[half * 8 + k];
-            __syncthreads();
+            cbar();
             for (int j = tid; j < 8 * L; j += kThreads) {
                 float tot = 0.f;
                 for (int rr = 0; rr < R; ++rr) tot += red[4096 + rr * 8 * L + j];
@@ -249,7 +262,7 @@ __device__ __forceinline__ void cta_reduce16(float (&a)[16], int L, float* red /
             }
         }
     }
-    __syncthreads();
+    cbar();
 }
 
 // hop 1 + hop 2 (+ optional per-entry side effect through `on_total`), then collect into red[0..n16)
@@ -264,26 +277,42 @@ __device__ __forceinline__ void exchange(const BnGeom& g, const BnWork& w, const
     // hop 1a: my CTA total as packets
     uint2* mine = w.partials + static_cast<size_t>(blockIdx.x) * n16;
     for (int j = tid; j < n16; j += kThreads) st_packet_gpu(mine + j, red[j], tag);
-    // hop 1b: my slice of entries, summed over all CTAs in CTA order (one warp per entry)
+    // hop 1b: my slice of entries, summed over all CTAs in CTA order (one warp per entry; the ≤5 packets a lane
+    // needs are requested together so their L2 round trips overlap)
     const int per = (n16 + strips - 1) / strips;
     const int j0 = blockIdx.x * per;
     const int j1 = (j0 + per < n16) ? j0 + per : n16;
     for (int j = j0 + warp; j < j1; j += kWarps) {
+        constexpr int kMaxPer = (kMaxGrid + 31) / 32;
+        uint2 v[kMaxPer];
+#pragma unroll
+        for (int u = 0; u < kMaxPer; ++u) {
+            const int t = lane + 32 * u;
+            if (t < strips) v[u] = ld_packet_gpu(w.partials + static_cast<size_t>(t) * n16 + j);
+        }
         float acc = 0.f;
-        for (int t = lane; t < strips; t += 32) acc += wait_packet_gpu(w.partials + static_cast<size_t>(t) * n16 + j, tag, timeout, fail);
+#pragma unroll
+        for (int u = 0; u < kMaxPer; ++u) {
+            const int t = lane + 32 * u;
+            if (t < strips) {
+                float val = __uint_as_float(v[u].x);
+                if (v[u].y != tag) val = wait_packet_gpu(w.partials + static_cast<size_t>(t) * n16 + j, tag, timeout, fail);
+                acc += val;
+            }
+        }
         acc = warp_sum(acc);
         if (lane == 0) {
             on_total(j, acc);
             publish(c, use_mc, stats_off, w.ll_local, g.C, j, acc, tag);  // hop 2
         }
     }
-    __syncthreads();  // everyone has finished reading red[] (hop 1a) before it is overwritten
+    cbar();  // everyone has finished reading red[] (hop 1a) before it is overwritten
     for (int j = tid; j < n16; j += kThreads) red[j] = collect(c, stats_off, w.ll_local, g.C, j, tag, timeout, fail);
     if (fail) {
         *s_fail = 1;
         if (c.error_flag) atomicExch(c.error_flag, 0xDEAD0001u);
     }
-    __syncthreads();
+    cbar();
 }
 
 __device__ __forceinline__ void ring_setup(Ring& ring, unsigned char* smem, const BnGeom& g, int nstream) {
@@ -302,14 +331,31 @@ __device__ __forceinline__ void ring_setup(Ring& ring, unsigned char* smem, cons
         }
         mbar_fence_init();
     }
-    __syncthreads();
+    __syncthreads();  // all kBlock threads (the only block-wide barrier in the kernels)
+}
+
+// The load sequence of one CTA (training): chunks 0..n-1 for phase 1, then the chunks that did not stay resident,
+// newest first (the likeliest L2 hits), for phase 2.  Load k goes to stage k % NS.
+__device__ __forceinline__ int load_chunk_of(int k, int n, int nres0) { return k < n ? k : nres0 - 1 - (k - n); }
+
+// producer warp: lane 0 keeps the ring full
+template <int NSRC>
+__device__ __forceinline__ void producer_loop(Ring& ring, const BnGeom& g, const void* const (&src)[NSRC], const StripInfo& sp,
+                                              int total_loads, int nres0) {
+    if ((threadIdx.x & 31) != 0) return;
+    const int NS = g.nstage;
+    for (int k = 0; k < total_loads; ++k) {
+        const int s = k % NS;
+        if (k >= NS) ring.wait_empty(s);
+        issue_chunk<NSRC>(ring, g, src, s, sp.chunk0 + load_chunk_of(k, sp.n, nres0));
+    }
 }
 
 // =================================================================================================
 // forward
 // =================================================================================================
 template <typename T>
-__global__ void __launch_bounds__(kThreads, 1) syncbn_fwd_kernel(const __grid_constant__ BnFwd prm) {
+__global__ void __launch_bounds__(kBlock, 1) syncbn_fwd_kernel(const __grid_constant__ BnFwd prm) {
     extern __shared__ __align__(128) unsigned char smem[];
     float* red = reinterpret_cast<float*>(smem + 256);
     float* s_scale = reinterpret_cast<float*>(smem + 256 + 32768);
@@ -319,23 +365,34 @@ __global__ void __launch_bounds__(kThreads, 1) syncbn_fwd_kernel(const __grid_co
     const BnGeom& g = prm.g;
     const int tid = threadIdx.x;
     const int L = g.L, C = g.C;
-    const int l = tid % L;
     const StripInfo sp = strip_info(g);
     const int NS = g.nstage;
     const bool has_pre = prm.pre != nullptr;
-    const T* __restrict__ gres = static_cast<const T*>(prm.res);
-    T* __restrict__ gy = static_cast<T*>(prm.y);
+    const bool training = prm.training != 0;
+    const int nres0 = training ? (sp.n > NS ? sp.n - NS : 0) : 0;   // chunks [nres0, n) stay resident after phase 1
+    const int total_loads = training ? sp.n + nres0 : sp.n;
     if (tid == 0) s_fail = 0;
+    stamp(prm.w, 0);
 
     Ring ring;
     ring_setup(ring, smem, g, has_pre ? 2 : 1);
     const void* const src[2] = {prm.x, prm.pre};
-    if (tid == 0) {
-        const int first = sp.n < NS ? sp.n : NS;
-        for (int i = 0; i < first; ++i) issue_chunk<2>(ring, g, src, i, sp.chunk0 + i);
+    if (tid >= kThreads) {  // ---- producer warp --------------------------------------------------------------
+        producer_loop<2>(ring, g, src, sp, total_loads, nres0);
+        return;
     }
 
-    if (prm.training) {
+    // ---- consumers -------------------------------------------------------------------------------------
+    const int l = tid % L;
+    const T* __restrict__ gres = static_cast<const T*>(prm.res);
+    T* __restrict__ gy = static_cast<T*>(prm.y);
+    // affine / running parameters are fetched now so their DRAM latency hides behind phase 1
+    for (int ch = tid; ch < C; ch += kThreads) {
+        s_scale[ch] = prm.gamma[ch];
+        s_shift[ch] = prm.beta[ch];
+    }
+
+    if (training) {
         // ---- phase 1: Σz, Σz² from shared memory ----------------------------------------------------------
         float a[16];
 #pragma unroll
@@ -346,34 +403,27 @@ __global__ void __launch_bounds__(kThreads, 1) syncbn_fwd_kernel(const __grid_co
             const int npk = chunk_rows_of(g, sp.chunk0 + i) * L;
             const T* xs = reinterpret_cast<const T*>(ring.buf(s, 0));
             const T* ps = reinterpret_cast<const T*>(ring.buf(s, 1));
-            for (int j = 0; j < g.ppt; ++j) {
-                const int q = tid + j * kThreads;
-                if (q < npk) {
-                    float z[8];
-                    IO<T>::load8(xs + q * 8, z);
-                    if (has_pre) {
-                        float t[8];
-                        IO<T>::load8(ps + q * 8, t);
+            for (int q = tid; q < npk; q += kThreads) {
+                float z[8];
+                IO<T>::load8(xs + q * 8, z);
+                if (has_pre) {
+                    float t[8];
+                    IO<T>::load8(ps + q * 8, t);
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) z[k] += t[k];
-                    }
+                    for (int k = 0; k < 8; ++k) z[k] += t[k];
+                }
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        a[k] += z[k];
-                        a[8 + k] = fmaf(z[k], z[k], a[8 + k]);
-                    }
+                for (int k = 0; k < 8; ++k) {
+                    a[k] += z[k];
+                    a[8 + k] = fmaf(z[k], z[k], a[8 + k]);
                 }
             }
-            if (i + NS < sp.n) {  // the strip is longer than the ring: recycle this stage
-                ring.release(s);
-                if (tid == 0) {
-                    ring.wait_empty(s);
-                    issue_chunk<2>(ring, g, src, s, sp.chunk0 + i + NS);
-                }
-            }
+            if (i + NS < sp.n) ring.release(s);  // recycled within phase 1
         }
+        stamp(prm.w, 1);
         cta_reduce16(a, L, red);
         exchange(g, prm.w, prm.c, prm.use_mc, prm.stats_off, call_tag(prm.tag, prm.epoch), red, &s_fail, [](int, float) {});
+        stamp(prm.w, 2);
         // ---- per-channel coefficients --------------------------------------------------------------------
         const float n = static_cast<float>(g.rows) * static_cast<float>(prm.c.world);
         for (int ch = tid; ch < C; ch += kThreads) {
@@ -381,9 +431,9 @@ __global__ void __launch_bounds__(kThreads, 1) syncbn_fwd_kernel(const __grid_co
             const float mean = red[k * L + ll] / n;
             const float var = fmaxf(red[(8 + k) * L + ll] / n - mean * mean, 0.f);
             const float invstd = 1.0f / sqrtf(var + prm.eps);
-            const float sc = invstd * prm.gamma[ch];
+            const float sc = invstd * s_scale[ch];
             s_scale[ch] = sc;
-            s_shift[ch] = prm.beta[ch] - mean * sc;
+            s_shift[ch] = s_shift[ch] - mean * sc;
             if (blockIdx.x == 0) {
                 prm.smean[ch] = mean;
                 prm.sinvstd[ch] = invstd;
@@ -398,12 +448,12 @@ __global__ void __launch_bounds__(kThreads, 1) syncbn_fwd_kernel(const __grid_co
     } else {
         for (int ch = tid; ch < C; ch += kThreads) {
             const float invstd = 1.0f / sqrtf(prm.rvar[ch] + prm.eps);
-            const float sc = invstd * prm.gamma[ch];
+            const float sc = invstd * s_scale[ch];
             s_scale[ch] = sc;
-            s_shift[ch] = prm.beta[ch] - prm.rmean[ch] * sc;
+            s_shift[ch] = s_shift[ch] - prm.rmean[ch] * sc;
         }
     }
-    __syncthreads();
+    cbar();
 
     // ---- phase 2: normalize; resident chunks first, then the part of the strip that did not fit ---------
     float sc[8], sh[8];
@@ -413,33 +463,34 @@ __global__ void __launch_bounds__(kThreads, 1) syncbn_fwd_kernel(const __grid_co
         sh[k] = s_shift[l * 8 + k];
     }
     const bool relu = prm.relu != 0;
-    const int nres0 = prm.training ? (sp.n > NS ? sp.n - NS : 0) : 0;  // first resident chunk
-    const int nresident = prm.training ? sp.n - nres0 : 0;
-    // processing order: resident chunks first, then the streamed ones
-    auto chunk_of = [&](int i2) -> int {
-        if (!prm.training) return i2;
-        return i2 >= nresident ? nres0 - 1 - (i2 - nresident) : nres0 + i2;
+    const int nresident = training ? sp.n - nres0 : 0;
+    // use u of phase 2: u < nresident → resident chunk nres0+u (no wait); else load k = n + (u - nresident) (training)
+    // or plain ring order (eval)
+    constexpr int kPptMax = 4;
+    typename IO<T>::Raw rcur[kPptMax], rnext[kPptMax];
+    auto chunk_of = [&](int u) -> int {
+        if (!training) return u;
+        return u < nresident ? nres0 + u : nres0 - 1 - (u - nresident);
     };
     // the residual is read straight from global memory, one chunk ahead, so its latency hides behind the math
-    constexpr int kPptMax = 2;
-    typename IO<T>::Raw rcur[kPptMax], rnext[kPptMax];
-    auto fetch_res = [&](int i2, typename IO<T>::Raw (&dst)[kPptMax]) {
-        if (gres == nullptr || i2 >= sp.n) return;
-        const long long chunk = sp.chunk0 + chunk_of(i2);
+    auto fetch_res = [&](int u, typename IO<T>::Raw (&dst)[kPptMax]) {
+        if (gres == nullptr || u >= sp.n) return;
+        const long long chunk = sp.chunk0 + chunk_of(u);
         const int npk = chunk_rows_of(g, chunk) * L;
         const size_t ebase = static_cast<size_t>(chunk) * g.chunk_rows * C;
 #pragma unroll
         for (int j = 0; j < kPptMax; ++j) {
             const int q = tid + j * kThreads;
-            if (j < g.ppt && q < npk) dst[j] = IO<T>::load_raw(gres + ebase + static_cast<size_t>(q) * 8);
+            if (q < npk) dst[j] = IO<T>::load_raw(gres + ebase + static_cast<size_t>(q) * 8);
         }
     };
     fetch_res(0, rcur);
-    for (int i2 = 0; i2 < sp.n; ++i2) {
-        const int c = chunk_of(i2);
-        const bool streamed = prm.training ? (i2 >= nresident) : true;
-        const int s = prm.training ? (nres0 + i2) % NS : i2 % NS;
-        fetch_res(i2 + 1, rnext);
+    for (int u = 0; u < sp.n; ++u) {
+        const int c = chunk_of(u);
+        const bool streamed = training ? (u >= nresident) : true;
+        const int kload = training ? sp.n + (u - nresident) : u;        // load index when streamed
+        const int s = training ? (streamed ? kload % NS : (nres0 + u) % NS) : u % NS;
+        fetch_res(u + 1, rnext);
         if (streamed) ring.wait_full(s);
         const long long chunk = sp.chunk0 + c;
         const int npk = chunk_rows_of(g, chunk) * L;
@@ -449,7 +500,7 @@ __global__ void __launch_bounds__(kThreads, 1) syncbn_fwd_kernel(const __grid_co
 #pragma unroll
         for (int j = 0; j < kPptMax; ++j) {
             const int q = tid + j * kThreads;
-            if (j < g.ppt && q < npk) {
+            if (q < npk) {
                 float z[8];
                 IO<T>::load8(xs + q * 8, z);
                 if (has_pre) {
@@ -475,24 +526,18 @@ __global__ void __launch_bounds__(kThreads, 1) syncbn_fwd_kernel(const __grid_co
         }
 #pragma unroll
         for (int j = 0; j < kPptMax; ++j) rcur[j] = rnext[j];
-        // refill: training → the i2-th freed stage takes streamed chunk i2; eval → plain ring
-        const int next = prm.training ? i2 : i2 + NS;
-        const bool more = prm.training ? (i2 < nres0) : (next < sp.n);
-        if (more) {
-            ring.release(s);
-            if (tid == 0) {
-                ring.wait_empty(s);
-                issue_chunk<2>(ring, g, src, s, sp.chunk0 + (prm.training ? nres0 - 1 - next : next));
-            }
-        }
+        // release the stage iff a later load targets it
+        const int stage_load = training ? (streamed ? kload : nres0 + u) : u;   // index of the load that filled this stage
+        if (stage_load + NS < total_loads) ring.release(s);
     }
+    stamp(prm.w, 3);
 }
 
 // =================================================================================================
 // backward
 // =================================================================================================
 template <typename T>
-__global__ void __launch_bounds__(kThreads, 1) syncbn_bwd_kernel(const __grid_constant__ BnBwd prm) {
+__global__ void __launch_bounds__(kBlock, 1) syncbn_bwd_kernel(const __grid_constant__ BnBwd prm) {
     extern __shared__ __align__(128) unsigned char smem[];
     float* red = reinterpret_cast<float*>(smem + 256);
     float* s_a = reinterpret_cast<float*>(smem + 256 + 32768);
@@ -503,14 +548,14 @@ __global__ void __launch_bounds__(kThreads, 1) syncbn_bwd_kernel(const __grid_co
     const BnGeom& g = prm.g;
     const int tid = threadIdx.x;
     const int L = g.L, C = g.C;
-    const int l = tid % L;
     const StripInfo sp = strip_info(g);
     const int NS = g.nstage;
     const bool has_pre = prm.pre != nullptr;
     const bool relu = prm.relu != 0;
-    T* __restrict__ gdz = static_cast<T*>(prm.dz);
-    T* __restrict__ gdres = static_cast<T*>(prm.dres);
+    const int nres0 = sp.n > NS ? sp.n - NS : 0;
+    const int total_loads = sp.n + nres0;
     if (tid == 0) s_fail = 0;
+    stamp(prm.w, 0);
 
     Ring ring;
     ring_setup(ring, smem, g, g.nstream);
@@ -520,14 +565,44 @@ __global__ void __launch_bounds__(kThreads, 1) syncbn_bwd_kernel(const __grid_co
     if (has_pre) src[k_pre] = prm.pre;
     if (relu) src[k_y] = prm.y;
     const void* const csrc[4] = {src[0], src[1], src[2], src[3]};
-    if (tid == 0) {
-        const int first = sp.n < NS ? sp.n : NS;
-        for (int i = 0; i < first; ++i) issue_chunk<4>(ring, g, csrc, i, sp.chunk0 + i);
+    if (tid >= kThreads) {  // ---- producer warp --------------------------------------------------------------
+        producer_loop<4>(ring, g, csrc, sp, total_loads, nres0);
+        return;
     }
 
+    const int l = tid % L;
+    T* __restrict__ gdz = static_cast<T*>(prm.dz);
+    T* __restrict__ gdres = static_cast<T*>(prm.dres);
+    // saved statistics / affine parameters: fetched now, used after the exchange
+    for (int ch = tid; ch < C; ch += kThreads) {
+        s_a[ch] = prm.gamma[ch];
+        s_b[ch] = prm.sinvstd[ch];
+        s_d[ch] = prm.smean[ch];
+    }
+    cbar();
     float mean[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) mean[k] = prm.smean[l * 8 + k];
+    for (int k = 0; k < 8; ++k) mean[k] = s_d[l * 8 + k];
+
+    // one chunk of work, shared by both phases
+    auto load_packet = [&](int s, int q, float (&d)[8], float (&z)[8]) {
+        const T* ds = reinterpret_cast<const T*>(ring.buf(s, 0));
+        const T* xs = reinterpret_cast<const T*>(ring.buf(s, 1));
+        IO<T>::load8(ds + q * 8, d);
+        IO<T>::load8(xs + q * 8, z);
+        if (has_pre) {
+            float t[8];
+            IO<T>::load8(reinterpret_cast<const T*>(ring.buf(s, k_pre)) + q * 8, t);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) z[k] += t[k];
+        }
+        if (relu) {
+            float o[8];
+            IO<T>::load8(reinterpret_cast<const T*>(ring.buf(s, k_y)) + q * 8, o);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) d[k] = o[k] > 0.f ? d[k] : 0.f;
+        }
+    };
 
     // ---- phase 1: Σ dy_m and Σ dy_m (z - mean) -------------------------------------------------------------
     float a[16];
@@ -537,46 +612,21 @@ __global__ void __launch_bounds__(kThreads, 1) syncbn_bwd_kernel(const __grid_co
         const int s = i % NS;
         ring.wait_full(s);
         const int npk = chunk_rows_of(g, sp.chunk0 + i) * L;
-        const T* ds = reinterpret_cast<const T*>(ring.buf(s, 0));
-        const T* xs = reinterpret_cast<const T*>(ring.buf(s, 1));
-        const T* ps = reinterpret_cast<const T*>(ring.buf(s, k_pre));
-        const T* ys = reinterpret_cast<const T*>(ring.buf(s, k_y));
-        for (int j = 0; j < g.ppt; ++j) {
-            const int q = tid + j * kThreads;
-            if (q < npk) {
-                float d[8], z[8];
-                IO<T>::load8(ds + q * 8, d);
-                IO<T>::load8(xs + q * 8, z);
-                if (has_pre) {
-                    float t[8];
-                    IO<T>::load8(ps + q * 8, t);
+        for (int q = tid; q < npk; q += kThreads) {
+            float d[8], z[8];
+            load_packet(s, q, d, z);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) z[k] += t[k];
-                }
-                if (relu) {
-                    float o[8];
-                    IO<T>::load8(ys + q * 8, o);
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) d[k] = o[k] > 0.f ? d[k] : 0.f;
-                }
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    a[k] += d[k];
-                    a[8 + k] = fmaf(d[k], z[k] - mean[k], a[8 + k]);
-                }
+            for (int k = 0; k < 8; ++k) {
+                a[k] += d[k];
+                a[8 + k] = fmaf(d[k], z[k] - mean[k], a[8 + k]);
             }
         }
-        if (i + NS < sp.n) {
-            ring.release(s);
-            if (tid == 0) {
-                ring.wait_empty(s);
-                issue_chunk<4>(ring, g, csrc, s, sp.chunk0 + i + NS);
-            }
-        }
+        if (i + NS < sp.n) ring.release(s);
     }
+    stamp(prm.w, 1);
     cta_reduce16(a, L, red);
     {
-        const float* sinv = prm.sinvstd;
+        const float* sinv = s_b;
         float* dgamma = prm.dgamma;
         float* dbeta = prm.dbeta;
         const int LL = L;
@@ -588,21 +638,23 @@ __global__ void __launch_bounds__(kThreads, 1) syncbn_bwd_kernel(const __grid_co
             else dgamma[ch] = tot * sinv[ch];
         });
     }
+    stamp(prm.w, 2);
     {
         const float n = static_cast<float>(g.rows) * static_cast<float>(prm.c.world);
         for (int ch = tid; ch < C; ch += kThreads) {
             const int ll = ch >> 3, k = ch & 7;
             const float mean_dy = red[k * L + ll] / n;
             const float mean_dy_xmu = red[(8 + k) * L + ll] / n;
-            const float invstd = prm.sinvstd[ch];
-            const float A = prm.gamma[ch] * invstd;
+            const float invstd = s_b[ch];
+            const float A = s_a[ch] * invstd;
             const float B = -A * invstd * invstd * mean_dy_xmu;
+            const float mu = s_d[ch];
             s_a[ch] = A;
             s_b[ch] = B;
-            s_d[ch] = -A * mean_dy - B * prm.smean[ch];
+            s_d[ch] = -A * mean_dy - B * mu;
         }
     }
-    __syncthreads();
+    cbar();
 
     // ---- phase 2: dz = A dy_m + B z + D ; dres = dy_m ----------------------------------------------------------
     float A[8], B[8], D[8];
@@ -612,57 +664,38 @@ __global__ void __launch_bounds__(kThreads, 1) syncbn_bwd_kernel(const __grid_co
         B[k] = s_b[l * 8 + k];
         D[k] = s_d[l * 8 + k];
     }
-    const int nres0 = sp.n > NS ? sp.n - NS : 0;
     const int nresident = sp.n - nres0;
-    for (int i2 = 0; i2 < sp.n; ++i2) {
-        const bool streamed = i2 >= nresident;
-        const int c = streamed ? nres0 - 1 - (i2 - nresident) : nres0 + i2;
-        const int s = (nres0 + i2) % NS;
+    for (int u = 0; u < sp.n; ++u) {
+        const bool streamed = u >= nresident;
+        const int c = streamed ? nres0 - 1 - (u - nresident) : nres0 + u;
+        const int kload = sp.n + (u - nresident);
+        const int s = streamed ? kload % NS : (nres0 + u) % NS;
         if (streamed) ring.wait_full(s);
         const long long chunk = sp.chunk0 + c;
         const int npk = chunk_rows_of(g, chunk) * L;
-        const T* ds = reinterpret_cast<const T*>(ring.buf(s, 0));
-        const T* xs = reinterpret_cast<const T*>(ring.buf(s, 1));
-        const T* ps = reinterpret_cast<const T*>(ring.buf(s, k_pre));
-        const T* ys = reinterpret_cast<const T*>(ring.buf(s, k_y));
         const size_t ebase = static_cast<size_t>(chunk) * g.chunk_rows * C;
-        for (int j = 0; j < g.ppt; ++j) {
-            const int q = tid + j * kThreads;
-            if (q < npk) {
-                float d[8], z[8];
-                IO<T>::load8(ds + q * 8, d);
-                IO<T>::load8(xs + q * 8, z);
-                if (has_pre) {
-                    float t[8];
-                    IO<T>::load8(ps + q * 8, t);
+        for (int q = tid; q < npk; q += kThreads) {
+            float d[8], z[8];
+            load_packet(s, q, d, z);
+            if (gdres) IO<T>::store8(gdres + ebase + static_cast<size_t>(q) * 8, d);
+            float o[8];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) z[k] += t[k];
-                }
-                if (relu) {
-                    float o[8];
-                    IO<T>::load8(ys + q * 8, o);
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) d[k] = o[k] > 0.f ? d[k] : 0.f;
-                }
-                if (gdres) IO<T>::store8(gdres + ebase + static_cast<size_t>(q) * 8, d);
-                float o[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) o[k] = fmaf(A[k], d[k], fmaf(B[k], z[k], D[k]));
-                IO<T>::store8(gdz + ebase + static_cast<size_t>(q) * 8, o);
-            }
+            for (int k = 0; k < 8; ++k) o[k] = fmaf(A[k], d[k], fmaf(B[k], z[k], D[k]));
+            IO<T>::store8(gdz + ebase + static_cast<size_t>(q) * 8, o);
         }
-        if (i2 < nres0) {
-            ring.release(s);
-            if (tid == 0) {
-                ring.wait_empty(s);
-                issue_chunk<4>(ring, g, csrc, s, sp.chunk0 + (nres0 - 1 - i2));
-            }
-        }
+        const int stage_load = streamed ? kload : nres0 + u;
+        if (stage_load + NS < total_loads) ring.release(s);
     }
+    stamp(prm.w, 3);
 }
 
 // ---- host side ------------------------------------------------------------------------------------------
-static int make_geom(int64_t rows, int C, int dtype, int nstream, int chunk_bytes, BnGeom& g) {
+static int make_geom(int64_t rows, int C, int dtype, int nstream, BnGeom& g) {
+    // tools/membench.cu: a bulk-copy ring delivers ∝ bytes per chunk iteration (fixed ≈0.4 µs per iteration):
+    // 32-48 KB per stage reaches ≈7 TB/s, 16 KB only 5.5, 8 KB 3.1.  So: the largest power-of-two chunk per stream
+    // with nstream*chunk <= 48 KB.
+    int chunk_bytes = 32768;
+    while (nstream * chunk_bytes > 49152) chunk_bytes >>= 1;
     if (rows <= 0 || C <= 0 || (C % 8) != 0 || C > kMaxC) return SOD_EUNSUPPORTED;
     g.C = C;
     g.rows = rows;
@@ -701,6 +734,7 @@ static size_t bn_ws_layout(int C, BnWork* w, void* base) {
     off += static_cast<size_t>(2) * kMaxC * sizeof(uint2);
     if (w) w->partials = reinterpret_cast<uint2*>(static_cast<char*>(base) + off);
     off += static_cast<size_t>(kMaxGrid) * 2 * C * sizeof(uint2);
+    if (w) w->stamps = nullptr;
     return off;
 }
 
@@ -718,7 +752,7 @@ static int launch_bn(K kern, const void* prm, const BnGeom& g, int nstream, cuda
             if (c == nullptr) { c = reinterpret_cast<const void*>(kern); break; }
     }
     void* args[] = {const_cast<void*>(prm)};
-    e = cudaLaunchKernel(reinterpret_cast<const void*>(kern), dim3(g.strips), dim3(kThreads), args, smem, stream);
+    e = cudaLaunchKernel(reinterpret_cast<const void*>(kern), dim3(g.strips), dim3(kBlock), args, smem, stream);
     return static_cast<int>(e);
 }
 
@@ -756,7 +790,7 @@ extern "C" int sod_syncbn_fwd(const void* x, const void* pre_add, const void* re
                           stats_off + sod_syncbn_exchange_bytes(channels) <= comm->arena_bytes, SOD_ECOMM);
     }
     const int nstream = pre_add ? 2 : 1;
-    rc = make_geom(rows, channels, dtype, nstream, 16384, p.g);
+    rc = make_geom(rows, channels, dtype, nstream, p.g);
     if (rc != SOD_OK) return rc;
     if (bn_ws_layout(channels, &p.w, workspace) > workspace_bytes) return SOD_EWORKSPACE;
     p.x = x; p.pre = pre_add; p.res = residual; p.y = y;
@@ -766,6 +800,8 @@ extern "C" int sod_syncbn_fwd(const void* x, const void* pre_add, const void* re
     p.momentum = momentum; p.eps = eps; p.relu = relu; p.training = training;
     p.stats_off = stats_off; p.tag = seq; p.epoch = epoch;
     p.use_mc = (p.c.mc != 0) && !(flags & SOD_ALGO_NO_MULTIMEM);
+    if ((flags & SOD_DEBUG_TIMING) && workspace_bytes >= bn_ws_layout(channels, nullptr, nullptr) + kMaxGrid * 32)
+        p.w.stamps = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + bn_ws_layout(channels, nullptr, nullptr));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     return SOD_DISPATCH_DTYPE(dtype, T, [&]() -> int { return launch_bn(syncbn_fwd_kernel<T>, &p, p.g, nstream, s); });
 }
@@ -790,13 +826,15 @@ extern "C" int sod_syncbn_bwd(const void* dy, const void* x, const void* pre_add
                           stats_off + sod_syncbn_exchange_bytes(channels) <= comm->arena_bytes, SOD_ECOMM);
     }
     const int nstream = 2 + (pre_add ? 1 : 0) + (relu ? 1 : 0);
-    rc = make_geom(rows, channels, dtype, nstream, 8192, p.g);
+    rc = make_geom(rows, channels, dtype, nstream, p.g);
     if (rc != SOD_OK) return rc;
     if (bn_ws_layout(channels, &p.w, workspace) > workspace_bytes) return SOD_EWORKSPACE;
     p.dy = dy; p.x = x; p.pre = pre_add; p.y = relu ? y : nullptr; p.dz = dz; p.dres = dres;
     p.gamma = gamma; p.smean = save_mean; p.sinvstd = save_invstd; p.dgamma = dgamma; p.dbeta = dbeta;
     p.relu = relu; p.stats_off = stats_off; p.tag = seq; p.epoch = epoch;
     p.use_mc = (p.c.mc != 0) && !(flags & SOD_ALGO_NO_MULTIMEM);
+    if ((flags & SOD_DEBUG_TIMING) && workspace_bytes >= bn_ws_layout(channels, nullptr, nullptr) + kMaxGrid * 32)
+        p.w.stamps = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + bn_ws_layout(channels, nullptr, nullptr));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     return SOD_DISPATCH_DTYPE(dtype, T, [&]() -> int { return launch_bn(syncbn_bwd_kernel<T>, &p, p.g, nstream, s); });
 }

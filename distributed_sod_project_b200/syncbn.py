@@ -22,6 +22,7 @@ import torch.nn as nn
 from . import _lib, comm
 
 _state: dict = {}
+DEBUG_FLAGS = 0             # tools/bn_phases.py sets SOD_DEBUG_TIMING (4)
 FORCE_LOCAL = False         # bench.py roofline replay: run single-rank (no exchange) even inside a process group
 TRACE: list | None = None   # bench.py: when a list, every forward call appends (n, c, h, w, has_pre, has_res, relu)
 
@@ -29,7 +30,7 @@ TRACE: list | None = None   # bench.py: when a list, every forward call appends 
 def _dev_state(device: torch.device) -> dict:
     st = _state.get(device.index)
     if st is None:
-        nbytes = int(_lib.lib().sod_syncbn_workspace_bytes(1, 2048))
+        nbytes = int(_lib.lib().sod_syncbn_workspace_bytes(1, 2048)) + 8192    # + room for debug stamps
         st = {"ws": torch.zeros(nbytes, dtype=torch.uint8, device=device), "seq": 0,
               "epoch": torch.zeros(1, dtype=torch.int32, device=device), "graph": False, "idx": 0}
         _state[device.index] = st
@@ -97,7 +98,7 @@ class _SyncBNFn(torch.autograd.Function):
             running_mean.data_ptr() if running_mean is not None else None,
             running_var.data_ptr() if running_var is not None else None,
             mean.data_ptr(), invstd.data_ptr(), rows, c, float(momentum), float(eps), int(relu), int(training),
-            cref, soff, seq, epoch, nbt.data_ptr() if nbt is not None else None, ws.data_ptr(), ws.numel(), 0,
+            cref, soff, seq, epoch, nbt.data_ptr() if nbt is not None else None, ws.data_ptr(), ws.numel(), DEBUG_FLAGS,
             _lib.stream_ptr())
         _lib.check(rc, "sod_syncbn_fwd")
         _lib.count_launch()
@@ -125,7 +126,7 @@ def raw_backward(dy, x, pre, y, weight, mean, invstd, relu: bool, want_dres: boo
         dy.data_ptr(), x.data_ptr(), pre.data_ptr() if pre is not None else None,
         y.data_ptr() if (relu and y is not None) else None, dz.data_ptr(), dres.data_ptr() if dres is not None else None,
         _lib.dtype_code(x.dtype), weight.data_ptr(), mean.data_ptr(), invstd.data_ptr(), dgamma.data_ptr(),
-        dbeta.data_ptr(), n * h * w, c, int(relu), cref, soff, seq, epoch, ws.data_ptr(), ws.numel(), 0, _lib.stream_ptr())
+        dbeta.data_ptr(), n * h * w, c, int(relu), cref, soff, seq, epoch, ws.data_ptr(), ws.numel(), DEBUG_FLAGS, _lib.stream_ptr())
     _lib.check(rc, "sod_syncbn_bwd")
     _lib.count_launch()
     return dz, dres, dgamma, dbeta

@@ -35,8 +35,9 @@ def _entry(rank, world, port, fn_name, args):
         dist.destroy_process_group()
 
 
-def _spawn(fn_name, world=2, args=()):
+def _spawn(fn_name, world=None, args=()):
     import torch.multiprocessing as mp
+    world = world or max(2, min(NGPU, int(os.environ.get("SOD_TEST_WORLD", "2"))))
     mp.spawn(_entry, args=(world, _free_port(), fn_name, args), nprocs=world, join=True)
 
 
@@ -172,6 +173,7 @@ def _w_step(rank, world):
     from distributed_sod_project_b200.synthetic import synth_batch
     g = np.load(os.path.join(ROOT, "tests", "golden", "step_res50_w2_s128.npz"))
     _, bs, size, iters = (int(v) for v in g["meta"])
+    golden_ok = world == 2          # the reference trajectory was generated for two ranks
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     tr = Trainer(model_name="res50", dtype=torch.float32, channels_last=True)
@@ -181,9 +183,11 @@ def _w_step(rank, world):
         from distributed_sod_project_b200.loss import get_total_loss
         loss, items = get_total_loss(preds, m.cuda(), tr.loss_funcs, unit_upstream=True)
         tr.optimizer.zero_grad(); loss.backward(); tr.optimizer.step()
-        want = float(g[f"loss{it}"][rank])
-        assert float(loss) == pytest.approx(want, rel=1e-3 if it < 2 else 5e-3), (rank, it, float(loss), want)
-        if it == 0:
+        assert np.isfinite(float(loss))
+        if golden_ok:
+            want = float(g[f"loss{it}"][rank])
+            assert float(loss) == pytest.approx(want, rel=1e-3 if it < 2 else 5e-3), (rank, it, float(loss), want)
+        if it == 0 and golden_ok:
             ref_l = g["logits0"][rank * bs:(rank + 1) * bs]
             got = preds.detach().float().cpu().numpy()
             assert np.abs(got - ref_l).max() / np.abs(ref_l).max() < 1e-3
@@ -211,9 +215,9 @@ def _w_stress(rank, world):
             time.sleep(0.01)                      # skew
         xi = x * (i + 1)
         y = bn.fused_forward(xi)
-        # both ranks constant ⇒ global mean = (i+1)*1.5, biased var = ((i+1)*0.5)^2 ⇒ y = ±1 (γ=1, β=0)
-        want = (-1.0 if rank == 0 else 1.0)
-        assert torch.allclose(y, torch.full_like(y, want), atol=1e-3), (i, float(y.mean()))
+        # rank r holds the constant (r+1)(i+1) ⇒ mean = (i+1)(W+1)/2, biased var = (i+1)²(W²-1)/12 (γ=1, β=0)
+        want = (rank + 1 - (world + 1) / 2) / ((world * world - 1) / 12) ** 0.5
+        assert torch.allclose(y, torch.full_like(y, want), atol=2e-3), (i, float(y.mean()), want)
     comm.small_arena().check_error()
 
 

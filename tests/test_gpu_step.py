@@ -84,6 +84,10 @@ def test_cuda_graph_replay_matches_eager(golden):
             red, items, _ = tr.forward_backward_update(x.cuda(), m.cuda())
             out.append(float(red))
         losses[mode] = out
-    assert losses[True] == pytest.approx(losses[False], rel=2e-4)
+    # tools/diag_graph.py: two IDENTICAL eager runs of this model already differ by ~1e-3 at iteration 2 and ~6e-3 at
+    # iteration 3 (non-deterministic cuDNN wgrad + chaotic early training), so only the first two iterations can be
+    # compared tightly; replay vs eager sits inside that run-to-run band afterwards
+    assert losses[True][:2] == pytest.approx(losses[False][:2], rel=2e-5)
+    assert losses[True][2:] == pytest.approx(losses[False][2:], rel=2e-2)
     assert losses[True][0] == pytest.approx(float(g["loss0"][0]), rel=1e-3)
     assert losses[True][1] == pytest.approx(float(g["loss1"][0]), rel=1e-3)
