@@ -354,7 +354,7 @@ __device__ __forceinline__ void producer_loop(Ring& ring, const BnGeom& g, const
 // =================================================================================================
 // forward
 // =================================================================================================
-template <typename T>
+template <typename T, int PPT, bool RES>
 __global__ void __launch_bounds__(kBlock, 1) syncbn_fwd_kernel(const __grid_constant__ BnFwd prm) {
     extern __shared__ __align__(128) unsigned char smem[];
     float* red = reinterpret_cast<float*>(smem + 256);
@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(kBlock, 1) syncbn_fwd_kernel(const __grid_cons
 
     // ---- consumers -------------------------------------------------------------------------------------
     const int l = tid % L;
-    const T* __restrict__ gres = static_cast<const T*>(prm.res);
+    const T* __restrict__ gres = RES ? static_cast<const T*>(prm.res) : nullptr;
     T* __restrict__ gy = static_cast<T*>(prm.y);
     // affine / running parameters are fetched now so their DRAM latency hides behind phase 1
     for (int ch = tid; ch < C; ch += kThreads) {
@@ -403,19 +403,35 @@ __global__ void __launch_bounds__(kBlock, 1) syncbn_fwd_kernel(const __grid_cons
             const int npk = chunk_rows_of(g, sp.chunk0 + i) * L;
             const T* xs = reinterpret_cast<const T*>(ring.buf(s, 0));
             const T* ps = reinterpret_cast<const T*>(ring.buf(s, 1));
-            for (int q = tid; q < npk; q += kThreads) {
-                float z[8];
-                IO<T>::load8(xs + q * 8, z);
-                if (has_pre) {
-                    float t[8];
-                    IO<T>::load8(ps + q * 8, t);
+            {
+                const int qb = tid;
+                typename IO<T>::Raw rx[PPT], rp[PPT];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) z[k] += t[k];
+                for (int j = 0; j < PPT; ++j) {
+                    const int q = qb + j * kThreads;
+                    if (q < npk) {
+                        rx[j] = IO<T>::load_raw(xs + q * 8);
+                        if (has_pre) rp[j] = IO<T>::load_raw(ps + q * 8);
+                    }
                 }
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    a[k] += z[k];
-                    a[8 + k] = fmaf(z[k], z[k], a[8 + k]);
+                for (int j = 0; j < PPT; ++j) {
+                    const int q = qb + j * kThreads;
+                    if (q < npk) {
+                        float z[8];
+                        IO<T>::unpack(rx[j], z);
+                        if (has_pre) {
+                            float t[8];
+                            IO<T>::unpack(rp[j], t);
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) z[k] += t[k];
+                        }
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            a[k] += z[k];
+                            a[8 + k] = fmaf(z[k], z[k], a[8 + k]);
+                        }
+                    }
                 }
             }
             if (i + NS < sp.n) ring.release(s);  // recycled within phase 1
@@ -466,20 +482,21 @@ __global__ void __launch_bounds__(kBlock, 1) syncbn_fwd_kernel(const __grid_cons
     const int nresident = training ? sp.n - nres0 : 0;
     // use u of phase 2: u < nresident → resident chunk nres0+u (no wait); else load k = n + (u - nresident) (training)
     // or plain ring order (eval)
-    constexpr int kPptMax = 4;
-    typename IO<T>::Raw rcur[kPptMax], rnext[kPptMax];
+    constexpr int kPptMax = PPT;
+    constexpr int kResBuf = RES ? PPT : 1;
+    typename IO<T>::Raw rcur[kResBuf], rnext[kResBuf];
     auto chunk_of = [&](int u) -> int {
         if (!training) return u;
         return u < nresident ? nres0 + u : nres0 - 1 - (u - nresident);
     };
     // the residual is read straight from global memory, one chunk ahead, so its latency hides behind the math
-    auto fetch_res = [&](int u, typename IO<T>::Raw (&dst)[kPptMax]) {
-        if (gres == nullptr || u >= sp.n) return;
+    auto fetch_res = [&](int u, typename IO<T>::Raw (&dst)[kResBuf]) {
+        if (!RES || u >= sp.n) return;
         const long long chunk = sp.chunk0 + chunk_of(u);
         const int npk = chunk_rows_of(g, chunk) * L;
         const size_t ebase = static_cast<size_t>(chunk) * g.chunk_rows * C;
 #pragma unroll
-        for (int j = 0; j < kPptMax; ++j) {
+        for (int j = 0; j < kResBuf; ++j) {
             const int q = tid + j * kThreads;
             if (q < npk) dst[j] = IO<T>::load_raw(gres + ebase + static_cast<size_t>(q) * 8);
         }
@@ -497,23 +514,32 @@ __global__ void __launch_bounds__(kBlock, 1) syncbn_fwd_kernel(const __grid_cons
         const T* xs = reinterpret_cast<const T*>(ring.buf(s, 0));
         const T* ps = reinterpret_cast<const T*>(ring.buf(s, 1));
         const size_t ebase = static_cast<size_t>(chunk) * g.chunk_rows * C;
+        typename IO<T>::Raw rx[kPptMax], rp[kPptMax];
+#pragma unroll
+        for (int j = 0; j < kPptMax; ++j) {
+            const int q = tid + j * kThreads;
+            if (q < npk) {
+                rx[j] = IO<T>::load_raw(xs + q * 8);
+                if (has_pre) rp[j] = IO<T>::load_raw(ps + q * 8);
+            }
+        }
 #pragma unroll
         for (int j = 0; j < kPptMax; ++j) {
             const int q = tid + j * kThreads;
             if (q < npk) {
                 float z[8];
-                IO<T>::load8(xs + q * 8, z);
+                IO<T>::unpack(rx[j], z);
                 if (has_pre) {
                     float t[8];
-                    IO<T>::load8(ps + q * 8, t);
+                    IO<T>::unpack(rp[j], t);
 #pragma unroll
                     for (int k = 0; k < 8; ++k) z[k] += t[k];
                 }
 #pragma unroll
                 for (int k = 0; k < 8; ++k) z[k] = fmaf(z[k], sc[k], sh[k]);
-                if (gres) {
+                if (RES) {
                     float t[8];
-                    IO<T>::unpack(rcur[j], t);
+                    IO<T>::unpack(rcur[RES ? j : 0], t);
 #pragma unroll
                     for (int k = 0; k < 8; ++k) z[k] += t[k];
                 }
@@ -525,7 +551,7 @@ __global__ void __launch_bounds__(kBlock, 1) syncbn_fwd_kernel(const __grid_cons
             }
         }
 #pragma unroll
-        for (int j = 0; j < kPptMax; ++j) rcur[j] = rnext[j];
+        for (int j = 0; j < kResBuf; ++j) rcur[j] = rnext[j];
         // release the stage iff a later load targets it
         const int stage_load = training ? (streamed ? kload : nres0 + u) : u;   // index of the load that filled this stage
         if (stage_load + NS < total_loads) ring.release(s);
@@ -584,12 +610,11 @@ __global__ void __launch_bounds__(kBlock, 1) syncbn_bwd_kernel(const __grid_cons
 #pragma unroll
     for (int k = 0; k < 8; ++k) mean[k] = s_d[l * 8 + k];
 
-    // one chunk of work, shared by both phases
+    // one packet of work, shared by both phases (measured: interleaving two packets per thread only added register
+    // pressure here — four streams per packet already give the scheduler independent loads)
     auto load_packet = [&](int s, int q, float (&d)[8], float (&z)[8]) {
-        const T* ds = reinterpret_cast<const T*>(ring.buf(s, 0));
-        const T* xs = reinterpret_cast<const T*>(ring.buf(s, 1));
-        IO<T>::load8(ds + q * 8, d);
-        IO<T>::load8(xs + q * 8, z);
+        IO<T>::load8(reinterpret_cast<const T*>(ring.buf(s, 0)) + q * 8, d);
+        IO<T>::load8(reinterpret_cast<const T*>(ring.buf(s, 1)) + q * 8, z);
         if (has_pre) {
             float t[8];
             IO<T>::load8(reinterpret_cast<const T*>(ring.buf(s, k_pre)) + q * 8, t);
@@ -690,11 +715,11 @@ __global__ void __launch_bounds__(kBlock, 1) syncbn_bwd_kernel(const __grid_cons
 }
 
 // ---- host side ------------------------------------------------------------------------------------------
-static int make_geom(int64_t rows, int C, int dtype, int nstream, BnGeom& g) {
+static int make_geom(int64_t rows, int C, int dtype, int nstream, BnGeom& g, int max_chunk = 32768) {
     // tools/membench.cu: a bulk-copy ring delivers ∝ bytes per chunk iteration (fixed ≈0.4 µs per iteration):
     // 32-48 KB per stage reaches ≈7 TB/s, 16 KB only 5.5, 8 KB 3.1.  So: the largest power-of-two chunk per stream
     // with nstream*chunk <= 48 KB.
-    int chunk_bytes = 32768;
+    int chunk_bytes = max_chunk;
     while (nstream * chunk_bytes > 49152) chunk_bytes >>= 1;
     if (rows <= 0 || C <= 0 || (C % 8) != 0 || C > kMaxC) return SOD_EUNSUPPORTED;
     g.C = C;
@@ -741,7 +766,7 @@ static size_t bn_ws_layout(int C, BnWork* w, void* base) {
 template <typename K>
 static int launch_bn(K kern, const void* prm, const BnGeom& g, int nstream, cudaStream_t stream) {
     const size_t smem = kSmemFixed + static_cast<size_t>(g.nstage) * nstream * g.chunk_bytes;
-    static thread_local const void* configured[8] = {nullptr};   // per kernel instantiation, once per thread
+    static thread_local const void* configured[32] = {nullptr};   // per kernel instantiation, once per thread
     cudaError_t e;
     bool done = false;
     for (const void* c : configured) done |= (c == reinterpret_cast<const void*>(kern));
@@ -790,7 +815,8 @@ extern "C" int sod_syncbn_fwd(const void* x, const void* pre_add, const void* re
                           stats_off + sod_syncbn_exchange_bytes(channels) <= comm->arena_bytes, SOD_ECOMM);
     }
     const int nstream = pre_add ? 2 : 1;
-    rc = make_geom(rows, channels, dtype, nstream, p.g);
+    // with a residual operand the kernel prefetches it through registers: keep that to 2 packets per thread
+    rc = make_geom(rows, channels, dtype, nstream, p.g, residual ? 16384 : 32768);
     if (rc != SOD_OK) return rc;
     if (bn_ws_layout(channels, &p.w, workspace) > workspace_bytes) return SOD_EWORKSPACE;
     p.x = x; p.pre = pre_add; p.res = residual; p.y = y;
@@ -803,7 +829,15 @@ extern "C" int sod_syncbn_fwd(const void* x, const void* pre_add, const void* re
     if ((flags & SOD_DEBUG_TIMING) && workspace_bytes >= bn_ws_layout(channels, nullptr, nullptr) + kMaxGrid * 32)
         p.w.stamps = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + bn_ws_layout(channels, nullptr, nullptr));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    return SOD_DISPATCH_DTYPE(dtype, T, [&]() -> int { return launch_bn(syncbn_fwd_kernel<T>, &p, p.g, nstream, s); });
+    return SOD_DISPATCH_DTYPE(dtype, T, [&]() -> int {
+        const bool r = residual != nullptr;
+        switch (p.g.ppt) {
+            case 1: return r ? launch_bn(syncbn_fwd_kernel<T, 1, true>, &p, p.g, nstream, s) : launch_bn(syncbn_fwd_kernel<T, 1, false>, &p, p.g, nstream, s);
+            case 2: return r ? launch_bn(syncbn_fwd_kernel<T, 2, true>, &p, p.g, nstream, s) : launch_bn(syncbn_fwd_kernel<T, 2, false>, &p, p.g, nstream, s);
+            case 4: return r ? static_cast<int>(SOD_EUNSUPPORTED) : launch_bn(syncbn_fwd_kernel<T, 4, false>, &p, p.g, nstream, s);
+            default: return static_cast<int>(SOD_EUNSUPPORTED);
+        }
+    });
 }
 
 extern "C" int sod_syncbn_bwd(const void* dy, const void* x, const void* pre_add, const void* y, void* dz, void* dres,
