@@ -85,7 +85,7 @@ struct BnBwd {
     void *dz, *dres;
     const float *gamma, *smean, *sinvstd;
     float *dgamma, *dbeta;
-    int relu;
+    int relu, accumulate;
     BnGeom g;
     BnWork w;
     CommDev c;
@@ -655,12 +655,18 @@ __global__ void __launch_bounds__(kBlock, 1) syncbn_bwd_kernel(const __grid_cons
         float* dgamma = prm.dgamma;
         float* dbeta = prm.dbeta;
         const int LL = L;
+        const bool accumulate = prm.accumulate != 0;
         // GPU-local totals are also the local parameter gradients (the gradient all-reduce averages them later)
         exchange(g, prm.w, prm.c, prm.use_mc, prm.stats_off, call_tag(prm.tag, prm.epoch), red, &s_fail, [=](int j, float tot) {
             const int k = j / LL, ll = j % LL;
             const int ch = ll * 8 + (k & 7);
-            if (k < 8) dbeta[ch] = tot;
-            else dgamma[ch] = tot * sinv[ch];
+            if (accumulate) {
+                if (k < 8) dbeta[ch] += tot;
+                else dgamma[ch] += tot * sinv[ch];
+            } else {
+                if (k < 8) dbeta[ch] = tot;
+                else dgamma[ch] = tot * sinv[ch];
+            }
         });
     }
     stamp(prm.w, 2);
@@ -866,6 +872,7 @@ extern "C" int sod_syncbn_bwd(const void* dy, const void* x, const void* pre_add
     p.dy = dy; p.x = x; p.pre = pre_add; p.y = relu ? y : nullptr; p.dz = dz; p.dres = dres;
     p.gamma = gamma; p.smean = save_mean; p.sinvstd = save_invstd; p.dgamma = dgamma; p.dbeta = dbeta;
     p.relu = relu; p.stats_off = stats_off; p.tag = seq; p.epoch = epoch;
+    p.accumulate = (flags & SOD_BN_ACCUMULATE_PARAM_GRADS) ? 1 : 0;
     p.use_mc = (p.c.mc != 0) && !(flags & SOD_ALGO_NO_MULTIMEM);
     if ((flags & SOD_DEBUG_TIMING) && workspace_bytes >= bn_ws_layout(channels, nullptr, nullptr) + kMaxGrid * 32)
         p.w.stamps = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + bn_ws_layout(channels, nullptr, nullptr));

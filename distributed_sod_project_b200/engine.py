@@ -21,13 +21,16 @@ class Trainer:
     def __init__(self, model_name: str = "res50", lr: float = 0.05, momentum: float = 0.9, weight_decay: float = 5e-4,
                  nesterov: bool = False, optim: str = "f3_trick", reduction: str = "mean", use_aux_loss: bool = True,
                  dtype: torch.dtype = torch.bfloat16, channels_last: bool = True, seed: int = 0,
-                 device: torch.device | None = None, report_items: bool = True, use_graph: bool = False):
+                 device: torch.device | None = None, report_items: bool = True, use_graph: bool = False,
+                 native_interpolate: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("the B200 engine needs a CUDA device")
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.world = comm.world_size()
         self.channels_last = channels_last
         self.report_items = report_items
+        from .network import blocks as _blocks
+        _blocks.INTERPOLATE_IN_ACTIVATION_DTYPE = bool(native_interpolate)
         init_seed(seed)                                                    # train.py:113
         model = getattr(network, model_name)().to(self.device)            # train.py:141
         if channels_last:

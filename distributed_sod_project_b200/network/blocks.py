@@ -42,10 +42,20 @@ def bn_act(bn: nn.Module, x: torch.Tensor, *, relu: bool = True,
     return F.relu(y) if relu else y
 
 
+# torch.autocast lists upsample_bilinear2d as an fp32 op: under bf16 autocast every interpolate becomes
+# cast-up → fp32 kernel → fp32 result that then drags the following adds into fp32 (≈2 ms of casts per iteration on
+# the TestModel).  The B200 engine sets this flag so the interpolation runs natively in the activation dtype
+# (the kernel still accumulates in fp32 internally; only the stored result is rounded to bf16).
+INTERPOLATE_IN_ACTIVATION_DTYPE = False
+
+
 def bilinear(x: torch.Tensor, **kw) -> torch.Tensor:
     """`cus_sample` of the reference (utils/tensor_ops.py:12-18): bilinear, align_corners=False."""
     if len(kw) != 1 or next(iter(kw)) not in ("size", "scale_factor"):
         raise ValueError("bilinear() takes exactly one of size= / scale_factor=")
+    if INTERPOLATE_IN_ACTIVATION_DTYPE and x.is_cuda and x.dtype != torch.float32 and torch.is_autocast_enabled():
+        with torch.autocast("cuda", enabled=False):
+            return F.interpolate(x, mode="bilinear", align_corners=False, **kw)
     return F.interpolate(x, mode="bilinear", align_corners=False, **kw)
 
 

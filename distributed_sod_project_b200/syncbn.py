@@ -103,30 +103,45 @@ class _SyncBNFn(torch.autograd.Function):
         _lib.check(rc, "sod_syncbn_fwd")
         _lib.count_launch()
         ctx.relu, ctx.has_pre, ctx.has_res = bool(relu), pre is not None, res is not None
+        ctx.weight_ref, ctx.bias_ref = weight, bias
         ctx.save_for_backward(x, pre, y if relu else None, weight, mean, invstd)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, pre, y, weight, mean, invstd = ctx.saved_tensors
-        dz, dres, dgamma, dbeta = raw_backward(_as_rows(dy).to(x.dtype), x, pre, y, weight, mean, invstd, ctx.relu, ctx.has_res)
+        # when γ/β already carry a bound fp32 .grad (FusedSGD's flat buffer) the kernel adds into it directly and
+        # autograd gets None: saves two AccumulateGrad launches per layer
+        wg, bg = getattr(ctx.weight_ref, "grad", None), getattr(ctx.bias_ref, "grad", None)
+        direct = (wg is not None and bg is not None and wg.dtype == torch.float32 and bg.dtype == torch.float32
+                  and wg.is_contiguous() and bg.is_contiguous() and ctx.weight_ref.requires_grad and ctx.bias_ref.requires_grad)
+        dz, dres, dgamma, dbeta = raw_backward(_as_rows(dy).to(x.dtype), x, pre, y, weight, mean, invstd, ctx.relu, ctx.has_res,
+                                               into=(wg, bg) if direct else None)
+        if direct:
+            return (dz, dz if ctx.has_pre else None, dres, None, None, None, None, None, None, None, None, None)
         return (dz, dz if ctx.has_pre else None, dres, dgamma.to(weight.dtype), dbeta.to(weight.dtype),
                 None, None, None, None, None, None, None)
 
 
-def raw_backward(dy, x, pre, y, weight, mean, invstd, relu: bool, want_dres: bool):
-    """one `sod_syncbn_bwd` launch on channels-last tensors; returns (dz, dres|None, dgamma, dbeta)"""
+def raw_backward(dy, x, pre, y, weight, mean, invstd, relu: bool, want_dres: bool, into=None):
+    """one `sod_syncbn_bwd` launch on channels-last tensors; returns (dz, dres|None, dgamma, dbeta).
+    `into=(weight_grad, bias_grad)`: accumulate the parameter gradients into those fp32 tensors instead."""
     n, c, h, w = x.shape
     dz = torch.empty_like(x)
     dres = torch.empty_like(x) if want_dres else None
-    dgamma = torch.empty(c, dtype=torch.float32, device=x.device)
-    dbeta = torch.empty(c, dtype=torch.float32, device=x.device)
+    if into is not None:
+        dgamma, dbeta = into
+        flags = DEBUG_FLAGS | _lib.SOD_BN_ACCUMULATE_PARAM_GRADS
+    else:
+        dgamma = torch.empty(c, dtype=torch.float32, device=x.device)
+        dbeta = torch.empty(c, dtype=torch.float32, device=x.device)
+        flags = DEBUG_FLAGS
     ws, seq, epoch, cref, soff = _next_call(x.device)
     rc = _lib.lib().sod_syncbn_bwd(
         dy.data_ptr(), x.data_ptr(), pre.data_ptr() if pre is not None else None,
         y.data_ptr() if (relu and y is not None) else None, dz.data_ptr(), dres.data_ptr() if dres is not None else None,
         _lib.dtype_code(x.dtype), weight.data_ptr(), mean.data_ptr(), invstd.data_ptr(), dgamma.data_ptr(),
-        dbeta.data_ptr(), n * h * w, c, int(relu), cref, soff, seq, epoch, ws.data_ptr(), ws.numel(), DEBUG_FLAGS, _lib.stream_ptr())
+        dbeta.data_ptr(), n * h * w, c, int(relu), cref, soff, seq, epoch, ws.data_ptr(), ws.numel(), flags, _lib.stream_ptr())
     _lib.check(rc, "sod_syncbn_bwd")
     _lib.count_launch()
     return dz, dres, dgamma, dbeta

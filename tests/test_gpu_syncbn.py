@@ -125,3 +125,22 @@ def test_repeated_calls_are_deterministic():
     x = _mk((16, 256, 20, 20), torch.bfloat16, 11)
     ys = [bn.fused_forward(x, relu=True).clone() for _ in range(5)]
     assert all(torch.equal(ys[0], y) for y in ys[1:])
+
+
+def test_param_grads_accumulate_into_bound_grad():
+    """with γ/β .grad pre-bound (FusedSGD's flat buffer) the kernel adds into them and autograd receives None"""
+    bn = _bn(64)
+    x = _mk((4, 64, 9, 9), torch.float32, 21).requires_grad_(True)
+    dy = _mk((4, 64, 9, 9), torch.float32, 22)
+    bn.fused_forward(x, relu=True).backward(dy)
+    want_w, want_b = bn.weight.grad.clone(), bn.bias.grad.clone()
+    bn2 = _bn(64)
+    bn2.weight.grad = torch.full_like(bn2.weight, 0.5)
+    bn2.bias.grad = torch.full_like(bn2.bias, -0.25)
+    wptr = bn2.weight.grad.data_ptr()
+    x2 = x.detach().clone().requires_grad_(True)
+    bn2.fused_forward(x2, relu=True).backward(dy)
+    assert bn2.weight.grad.data_ptr() == wptr
+    assert torch.allclose(bn2.weight.grad, want_w + 0.5, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(bn2.bias.grad, want_b - 0.25, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(x2.grad, x.grad)
