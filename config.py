@@ -65,3 +65,8 @@ user_config = {
     "synthetic": True,
     "synthetic_iters_per_epoch": 20,
 }
+
+# test hook: SOD_CONFIG_JSON='{"epoch_num": 1, ...}' overrides keys without editing this file
+if os.environ.get("SOD_CONFIG_JSON"):
+    import json as _json
+    user_config.update(_json.loads(os.environ["SOD_CONFIG_JSON"]))

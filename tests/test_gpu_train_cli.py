@@ -1,0 +1,34 @@
+"""The reference's command line (`python train.py -ng N`) drives the B200 engine end to end."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(ngpus, overrides, port):
+    env = dict(os.environ, SOD_CONFIG_JSON=json.dumps(overrides))
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "train.py"), "-ng", str(ngpus), "-p", str(port)], cwd=ROOT, env=env,
+                         capture_output=True, text=True, timeout=500)
+    assert out.returncode == 0, out.stderr[-3000:]
+    return out.stdout
+
+
+def test_train_cli_single_gpu_multiscale(tmp_path):
+    out = _run(1, {"epoch_num": 2, "synthetic_iters_per_epoch": 3, "batch_size": 4, "print_freq": 1, "save_freq": 0, "is_distributed": False,
+                   "size_list": [128, 192], "input_size": 192, "model": "cp_res50", "output_name": "output"}, 29701)
+    assert "End Training" in out and out.count("[I:") == 6 and "Lr:0.0050000,0.0500000" in out
+    ckpt = [l for l in out.splitlines() if "img/s" in l]
+    assert len(ckpt) == 2
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_train_cli_two_gpus_graph():
+    out = _run(2, {"epoch_num": 1, "synthetic_iters_per_epoch": 4, "batch_size": 8, "print_freq": 2, "save_freq": 0,
+                   "input_size": 128, "model": "res50", "cuda_graph": True}, 29702)
+    assert "End Training" in out and out.count("[I:") == 2
