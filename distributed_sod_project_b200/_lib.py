@@ -45,10 +45,11 @@ _PROTOTYPES = {
                                            C.c_void_p, C.c_size_t, C.c_void_p]),
     "sod_scale_by_device_scalar": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
     "sod_comm_flag_bytes": (C.c_size_t, []),
-    "sod_sgd_momentum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(sod_sgd_segment), C.c_int,
-                                   C.c_float, C.c_void_p, C.c_int, C.c_void_p]),
-    "sod_allreduce_sgd": (C.c_int, [C.POINTER(sod_comm), C.c_uint64, C.c_uint64, C.c_void_p, C.c_int64,
+    "sod_sgd_momentum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                   C.POINTER(sod_sgd_segment), C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_void_p]),
+    "sod_allreduce_sgd": (C.c_int, [C.POINTER(sod_comm), C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int64,
                                     C.POINTER(sod_sgd_segment), C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_void_p]),
+    "sod_grad_merge_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "sod_grad_nonfinite": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "sod_allreduce_f32": (C.c_int, [C.POINTER(sod_comm), C.c_uint64, C.c_int64, C.c_float, C.c_int, C.c_int, C.c_void_p]),
     "sod_syncbn_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int]),

@@ -21,7 +21,44 @@ _cfg = {"enabled": False, "dtype": torch.bfloat16, "scale": 1.0, "dynamic": Fals
         "growth_interval": 2000, "found_inf": None}
 
 
-def initialize(model, optimizer=None, opt_level: str = "O1", dtype: torch.dtype = torch.bfloat16, **_ignored):
+def _install_shadow_weights(model, flat) -> int:
+    """Point every Conv2d whose parameters live in `flat` at the bf16 shadow copy: under autocast the convolution
+    then takes its weight without a per-iteration cast kernel, and autograd accumulates the (bf16) weight gradient
+    straight into the flat bf16 gradient buffer the fused step consumes.  fp32 masters stay the module Parameters
+    (state_dict / checkpoints / optimizer groups are unaffected)."""
+    import torch.nn as nn
+    managed = {id(p) for p, _ in flat.slots}
+    count = 0
+    for m in model.modules():
+        if not isinstance(m, nn.Conv2d) or id(m.weight) not in managed or hasattr(m, "_sod_w16"):
+            continue
+        w16 = flat.view16(flat.shadow16, m.weight)
+        w16.requires_grad_(m.weight.requires_grad)
+        if m.weight.requires_grad:
+            w16.grad = flat.view16(flat.grad16, m.weight)
+        m._sod_w16, m._sod_b16 = w16, None
+        if m.bias is not None and id(m.bias) in managed:
+            b16 = flat.view16(flat.shadow16, m.bias)
+            b16.requires_grad_(m.bias.requires_grad)
+            if m.bias.requires_grad:
+                b16.grad = flat.view16(flat.grad16, m.bias)
+            m._sod_b16 = b16
+        elif m.bias is not None:
+            continue
+
+        def forward(x, m=m):
+            if torch.is_autocast_enabled() and x.is_cuda:
+                return m._conv_forward(x, m._sod_w16, m._sod_b16)
+            return m._conv_forward(x, m.weight, m.bias)         # eval / fp32 use: the master copy
+
+        m.forward = forward
+        count += 1
+    model.register_load_state_dict_post_hook(lambda mod, incompatible: flat.refresh_shadow())
+    return count
+
+
+def initialize(model, optimizer=None, opt_level: str = "O1", dtype: torch.dtype = torch.bfloat16, shadow_weights: bool = True,
+               **_ignored):
     """Returns (model, optimizer) like apex. The model's forward runs under autocast(dtype)."""
     if opt_level not in ("O0", "O1"):
         raise _lib.SodError(f"opt_level {opt_level!r}: only O0/O1 semantics are provided")
@@ -38,6 +75,9 @@ def initialize(model, optimizer=None, opt_level: str = "O1", dtype: torch.dtype 
                 return inner(*a, **k)
 
         model.forward = autocast_forward
+        if shadow_weights and dtype == torch.bfloat16 and isinstance(optimizer, FusedSGD) and optimizer.flat.param.is_cuda:
+            optimizer.flat.enable_shadow(dtype)
+            _install_shadow_weights(model, optimizer.flat)
     return (model, optimizer) if optimizer is not None else model
 
 

@@ -66,8 +66,22 @@ __device__ __forceinline__ void sgd_update(float4& p, float4& v, const float4& g
 // ------------------------------------------------------------------------------------------------
 // world == 1
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 bf16x4_to_f32(uint2 u) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+    const float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ uint2 f32x4_to_bf16(const float4& f) {
+    uint2 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+    h[0] = __floats2bfloat162_rn(f.x, f.y);
+    h[1] = __floats2bfloat162_rn(f.z, f.w);
+    return u;
+}
+
 __global__ void __launch_bounds__(kThreads) sgd_local_kernel(float4* __restrict__ p, float4* __restrict__ v,
-                                                             float4* __restrict__ g, long long nvec,
+                                                             float4* __restrict__ g, uint2* __restrict__ g16,
+                                                             uint2* __restrict__ shadow, long long nvec,
                                                              const __grid_constant__ SegTable segs, float inv_scale,
                                                              const uint32_t* found_inf, int zero_grad) {
     const bool skip = (found_inf != nullptr && *found_inf != 0);  // amp overflow: no update, but still clear g
@@ -83,6 +97,10 @@ __global__ void __launch_bounds__(kThreads) sgd_local_kernel(float4* __restrict_
             sidx[u] = -1;
             if (i < nvec) {
                 gv[u] = g[i];
+                if (g16 != nullptr) {   // gradients autograd left in bf16: fold them in here (the "cast" of amp O1)
+                    const float4 h = bf16x4_to_f32(g16[i]);
+                    gv[u].x += h.x; gv[u].y += h.y; gv[u].z += h.z; gv[u].w += h.w;
+                }
                 if (!skip && cur.find(segs, i)) {
                     sidx[u] = cur.s;
                     pv[u] = p[i];
@@ -100,9 +118,27 @@ __global__ void __launch_bounds__(kThreads) sgd_local_kernel(float4* __restrict_
                     sgd_update(pv[u], vv[u], gs, segs.lr[s], segs.wd[s], segs.mu[s]);
                     p[i] = pv[u];
                     v[i] = vv[u];
+                    if (shadow != nullptr) shadow[i] = f32x4_to_bf16(pv[u]);
                 }
-                if (zero_grad) g[i] = zero;
+                if (zero_grad) {
+                    g[i] = zero;
+                    if (g16 != nullptr) g16[i] = make_uint2(0u, 0u);
+                }
             }
+        }
+    }
+}
+
+__global__ void grad_merge_bf16_kernel(float4* __restrict__ g, uint2* __restrict__ g16, long long nvec) {
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const uint2 raw = g16[i];
+        if ((raw.x | raw.y) != 0u) {   // most of the flat buffer (BN parameters, padding) never sees a bf16 gradient
+            float4 a = g[i];
+            const float4 h = bf16x4_to_f32(raw);
+            a.x += h.x; a.y += h.y; a.z += h.z; a.w += h.w;
+            g[i] = a;
+            g16[i] = make_uint2(0u, 0u);
         }
     }
 }
@@ -147,7 +183,7 @@ __global__ void __launch_bounds__(kThreads) allreduce_sgd_kernel(const __grid_co
                                                                  uint64_t param_off, float4* __restrict__ mom,
                                                                  long long nvec, const __grid_constant__ SegTable segs,
                                                                  float scale, const uint32_t* found_inf,
-                                                                 int zero_grad) {
+                                                                 int zero_grad, uint2* __restrict__ shadow) {
     const bool skip = (found_inf != nullptr && *found_inf != 0);  // caller guarantees identical on all ranks
     // every rank's backward has finished writing its gradients
     if (!comm_block_barrier(c, 0, blockIdx.x)) return;
@@ -184,15 +220,19 @@ __global__ void __launch_bounds__(kThreads) allreduce_sgd_kernel(const __grid_co
     // every rank's parameter shard has landed everywhere (and every peer is done reading my gradients)
     if (!comm_block_barrier(c, 0, blockIdx.x)) return;
 
-    if (zero_grad) {
-        // this block's peers read exactly the vectors {q*shard + blockIdx*kThreads + t + k*stride}: safe to clear now
+    if (zero_grad || shadow != nullptr) {
+        // this block's peers read / wrote exactly the vectors {q*shard + blockIdx*kThreads + t + k*stride}: after the
+        // barrier it is safe to clear those gradients, and the parameters that landed there are final — refresh the
+        // local bf16 shadow from them
         float4* g_local = reinterpret_cast<float4*>(c.peer[c.rank] + grad_off);
         const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int q = 0; q < c.world; ++q) {
             const long long qlo = shard * q;
             const long long qhi = (qlo + shard < nvec) ? qlo + shard : nvec;
-            for (long long i = qlo + static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < qhi; i += stride)
-                g_local[i] = zero;
+            for (long long i = qlo + static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < qhi; i += stride) {
+                if (zero_grad) g_local[i] = zero;
+                if (shadow != nullptr && !skip) shadow[i] = f32x4_to_bf16(p_local[i]);
+            }
         }
     }
 }
@@ -264,11 +304,13 @@ static unsigned comm_grid(long long vecs_per_rank) {
 }  // namespace
 }  // namespace sod
 
-extern "C" int sod_sgd_momentum(float* param, float* mom, float* grad, int64_t n, const sod_sgd_segment* segs,
-                                int nseg, float inv_scale, const uint32_t* found_inf, int flags, void* stream) {
+extern "C" int sod_sgd_momentum(float* param, float* mom, float* grad, void* grad16, void* shadow16, int64_t n,
+                                const sod_sgd_segment* segs, int nseg, float inv_scale, const uint32_t* found_inf,
+                                int flags, void* stream) {
     using namespace sod;
     SOD_CHECK_ARG(param && mom && grad && n > 0, SOD_EINVAL);
     SOD_CHECK_ARG((n & 3) == 0 && aligned16(param) && aligned16(mom) && aligned16(grad), SOD_EALIGN);
+    SOD_CHECK_ARG((!grad16 || aligned16(grad16)) && (!shadow16 || aligned16(shadow16)), SOD_EALIGN);
     SegTable t;
     int rc = make_seg_table(segs, nseg, n, t);
     if (rc != SOD_OK) return rc;
@@ -277,8 +319,9 @@ extern "C" int sod_sgd_momentum(float* param, float* mom, float* grad, int64_t n
     const long long cap = 2ll * dev_info().sm_count;
     if (blocks > cap) blocks = cap;
     sgd_local_kernel<<<static_cast<unsigned>(blocks), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<float4*>(param), reinterpret_cast<float4*>(mom), reinterpret_cast<float4*>(grad), nvec, t,
-        inv_scale, found_inf, (flags & SOD_SGD_ZERO_GRAD) ? 1 : 0);
+        reinterpret_cast<float4*>(param), reinterpret_cast<float4*>(mom), reinterpret_cast<float4*>(grad),
+        reinterpret_cast<uint2*>(grad16), reinterpret_cast<uint2*>(shadow16), nvec, t, inv_scale, found_inf,
+        (flags & SOD_SGD_ZERO_GRAD) ? 1 : 0);
     return static_cast<int>(cudaGetLastError());
 }
 
@@ -294,9 +337,21 @@ extern "C" int sod_grad_nonfinite(const float* grad, int64_t n, uint32_t* found_
     return static_cast<int>(cudaGetLastError());
 }
 
-extern "C" int sod_allreduce_sgd(const sod_comm* comm, uint64_t grad_off, uint64_t param_off, float* mom, int64_t n,
-                                 const sod_sgd_segment* segs, int nseg, float inv_scale, const uint32_t* found_inf,
-                                 int flags, void* stream) {
+extern "C" int sod_grad_merge_bf16(float* grad, void* grad16, int64_t n, void* stream) {
+    using namespace sod;
+    SOD_CHECK_ARG(grad && grad16 && n > 0, SOD_EINVAL);
+    SOD_CHECK_ARG((n & 3) == 0 && aligned16(grad) && aligned16(grad16), SOD_EALIGN);
+    const long long nvec = n >> 2;
+    long long blocks = (nvec + 1023) / 1024;
+    if (blocks > 8ll * dev_info().sm_count) blocks = 8ll * dev_info().sm_count;
+    grad_merge_bf16_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<float4*>(grad), reinterpret_cast<uint2*>(grad16), nvec);
+    return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int sod_allreduce_sgd(const sod_comm* comm, uint64_t grad_off, uint64_t param_off, float* mom, void* shadow16,
+                                 int64_t n, const sod_sgd_segment* segs, int nseg, float inv_scale,
+                                 const uint32_t* found_inf, int flags, void* stream) {
     using namespace sod;
     SOD_CHECK_ARG(comm && mom && n > 0, SOD_EINVAL);
     SOD_CHECK_ARG((n & 3) == 0 && aligned16(mom) && (grad_off & 15) == 0 && (param_off & 15) == 0, SOD_EALIGN);
@@ -317,10 +372,10 @@ extern "C" int sod_allreduce_sgd(const sod_comm* comm, uint64_t grad_off, uint64
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (mc)
         allreduce_sgd_kernel<true><<<grid, kThreads, 0, s>>>(c, grad_off, param_off, reinterpret_cast<float4*>(mom), nvec, t,
-                                                             scale, found_inf, zg);
+                                                             scale, found_inf, zg, reinterpret_cast<uint2*>(shadow16));
     else
         allreduce_sgd_kernel<false><<<grid, kThreads, 0, s>>>(c, grad_off, param_off, reinterpret_cast<float4*>(mom), nvec, t,
-                                                              scale, found_inf, zg);
+                                                              scale, found_inf, zg, reinterpret_cast<uint2*>(shadow16));
     return static_cast<int>(cudaGetLastError());
 }
 

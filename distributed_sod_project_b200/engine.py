@@ -22,7 +22,7 @@ class Trainer:
                  nesterov: bool = False, optim: str = "f3_trick", reduction: str = "mean", use_aux_loss: bool = True,
                  dtype: torch.dtype = torch.bfloat16, channels_last: bool = True, seed: int = 0,
                  device: torch.device | None = None, report_items: bool = True, use_graph: bool = False,
-                 native_interpolate: bool = True):
+                 native_interpolate: bool = True, shadow_weights: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("the B200 engine needs a CUDA device")
         self.device = device or torch.device("cuda", torch.cuda.current_device())
@@ -40,7 +40,8 @@ class Trainer:
         model = convert_syncbn_model(model)                                # train.py:180 (also at world 1: fused BN)
         self.use_amp = dtype != torch.float32
         if self.use_amp:
-            model, self.optimizer = amp.initialize(model, self.optimizer, opt_level="O1", dtype=dtype)  # train.py:183
+            model, self.optimizer = amp.initialize(model, self.optimizer, opt_level="O1", dtype=dtype,
+                                                   shadow_weights=shadow_weights)                  # train.py:183
         if self.world > 1:
             model = DistributedDataParallel(model, delay_allreduce=True)   # train.py:185
         self.model = model
@@ -90,6 +91,7 @@ class Trainer:
         # the warm-up iterations (allocator, cuDNN autotune, autograd thread) must not move the training state
         flat = self.optimizer.flat
         snap = [flat.param.clone(), flat.mom.clone()] + [b.clone() for b in self.module.buffers()]
+        shadow_snap = flat.shadow16.clone() if flat.shadow16 is not None else None
         steps, stepped = self.optimizer.steps, self.optimizer._stepped
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -101,6 +103,8 @@ class Trainer:
             flat.param.copy_(snap[0]); flat.mom.copy_(snap[1])
             for b, old in zip(self.module.buffers(), snap[2:]):
                 b.copy_(old)
+            if shadow_snap is not None:
+                flat.shadow16.copy_(shadow_snap)
         self.optimizer.steps, self.optimizer._stepped = steps, stepped
         if self.world > 1:
             torch.distributed.barrier()

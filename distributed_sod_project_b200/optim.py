@@ -58,7 +58,31 @@ class FlatParams:
         self.mom = torch.zeros(off, dtype=torch.float32, device=dev)
         self.arena = None          # set by DistributedDataParallel when world > 1
         self.param_off = self.grad_off = 0
+        self.shadow16: torch.Tensor | None = None   # bf16 copy of `param`, refreshed by the fused step (amp O1 shadow)
+        self.grad16: torch.Tensor | None = None     # bf16 gradients autograd accumulates for the shadowed tensors
         self._bind(copy_from_params=True)
+
+    # -- mixed precision: bf16 shadow of the fp32 master ---------------------------------------------------
+    def enable_shadow(self, dtype: torch.dtype = torch.bfloat16) -> None:
+        if dtype != torch.bfloat16:
+            raise _lib.SodError("the shadow copy is bf16 (fp16 needs dynamic loss scaling: handled without a shadow)")
+        if self.shadow16 is None:
+            self.shadow16 = torch.zeros(self.numel, dtype=dtype, device=self.device)
+            self.grad16 = torch.zeros(self.numel, dtype=dtype, device=self.device)
+        self.refresh_shadow()
+
+    def refresh_shadow(self) -> None:
+        if self.shadow16 is not None:
+            self.shadow16.copy_(self.param)
+
+    def offset_of(self, p: nn.Parameter) -> int:
+        for q, off in self.slots:
+            if q is p:
+                return off
+        raise KeyError("parameter not managed")
+
+    def view16(self, buf: torch.Tensor, p: nn.Parameter) -> torch.Tensor:
+        return self._view(buf, self.offset_of(p), p.data)
 
     @staticmethod
     def _view(buf: torch.Tensor, off: int, p: torch.Tensor) -> torch.Tensor:
@@ -89,6 +113,7 @@ class FlatParams:
         self.param, self.grad = new_p, new_g
         self.arena, self.param_off, self.grad_off = arena, param_off, grad_off
         self._bind(copy_from_params=False)
+        self.refresh_shadow()
 
     def momentum_view(self, p: nn.Parameter) -> torch.Tensor:
         for q, off in self.slots:
@@ -116,9 +141,13 @@ class FusedSGD(Optimizer):
         self.inv_scale = 1.0                   # amp: 1/S for the coming step
         self.found_inf: torch.Tensor | None = None  # amp: device uint32 flag, or None
         self._grads_clean = True
-        self._clean_version = self.flat.grad._version
+        self._clean_version = self._grad_versions()
         self._stepped = False
         self.steps = 0
+
+    def _grad_versions(self):
+        f = self.flat
+        return (f.grad._version, f.grad16._version if f.grad16 is not None else -1, id(f.grad))
 
     # -- torch.optim.Optimizer protocol -------------------------------------------------------------------
     def zero_grad(self, set_to_none: bool = False):
@@ -126,8 +155,10 @@ class FusedSGD(Optimizer):
         Gradients stay bound as views — `set_to_none` is accepted and ignored."""
         # the fused step clears the buffer in-kernel; autograd's in-place accumulation bumps the (shared)
         # version counter of the flat buffer, so an unchanged version means nothing has written since
-        if not (self._grads_clean and self.flat.grad._version == self._clean_version):
+        if not (self._grads_clean and self._grad_versions() == self._clean_version):
             self.flat.grad.zero_()
+            if self.flat.grad16 is not None:
+                self.flat.grad16.zero_()
         self._grads_clean = False
         # autograd may have replaced a .grad (e.g. after an external `p.grad = None`): rebind
         for p, off in self.flat.slots:
@@ -156,18 +187,24 @@ class FusedSGD(Optimizer):
             raise _lib.SodError("FusedSGD.step needs CUDA parameters (no CPU fallback)")
         segs, n = self._segments()
         finf = self.found_inf.data_ptr() if self.found_inf is not None else None
+        g16 = f.grad16.data_ptr() if f.grad16 is not None else None
+        s16 = f.shadow16.data_ptr() if f.shadow16 is not None else None
         if f.arena is None:
-            rc = _lib.lib().sod_sgd_momentum(f.param.data_ptr(), f.mom.data_ptr(), f.grad.data_ptr(), f.numel, segs, n,
-                                             float(self.inv_scale), finf, _lib.SOD_SGD_ZERO_GRAD, _lib.stream_ptr())
+            rc = _lib.lib().sod_sgd_momentum(f.param.data_ptr(), f.mom.data_ptr(), f.grad.data_ptr(), g16, s16, f.numel,
+                                             segs, n, float(self.inv_scale), finf, _lib.SOD_SGD_ZERO_GRAD, _lib.stream_ptr())
             _lib.check(rc, "sod_sgd_momentum")
         else:
             a = f.arena
-            rc = _lib.lib().sod_allreduce_sgd(a.ref, f.grad_off, f.param_off, f.mom.data_ptr(), f.numel, segs, n,
+            if g16 is not None:     # peers read the fp32 symmetric buffer: fold the local bf16 gradients in first
+                rc = _lib.lib().sod_grad_merge_bf16(f.grad.data_ptr(), g16, f.numel, _lib.stream_ptr())
+                _lib.check(rc, "sod_grad_merge_bf16")
+                _lib.count_launch()
+            rc = _lib.lib().sod_allreduce_sgd(a.ref, f.grad_off, f.param_off, f.mom.data_ptr(), s16, f.numel, segs, n,
                                               float(self.inv_scale), finf, _lib.SOD_SGD_ZERO_GRAD, _lib.stream_ptr())
             _lib.check(rc, "sod_allreduce_sgd")
         _lib.count_launch()
         self._grads_clean = True
-        self._clean_version = self.flat.grad._version
+        self._clean_version = self._grad_versions()
         self._stepped = True
         self.steps += 1
 
@@ -194,6 +231,7 @@ class FusedSGD(Optimizer):
                         loaded = True
         self.state.clear()
         self._stepped = self._stepped or loaded
+        self.flat.refresh_shadow()
 
     def __repr__(self):
         return super().__repr__().replace("FusedSGD", "FusedSGD[sm_100a flat]", 1)

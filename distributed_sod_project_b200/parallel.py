@@ -52,6 +52,7 @@ class DistributedDataParallel(nn.Module):
         self.flat.relocate(self.arena, p_off, g_off)
         # every rank starts from rank 0's weights / buffers (apex DDP ctor)
         dist.broadcast(self.flat.param, 0, group=process_group)
+        self.flat.refresh_shadow()
         for b in module.buffers():
             dist.broadcast(b, 0, group=process_group)
         if self._explicit_allreduce:

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SOD_ABI_VERSION 2
+#define SOD_ABI_VERSION 3
 #define SOD_MAX_WORLD 8
 #define SOD_MAX_SEGMENTS 16
 #define SOD_COMM_MAX_BLOCKS 1024   /* flag rows per channel */
@@ -98,7 +98,13 @@ size_t sod_comm_flag_bytes(void);
  * in rank order), updates its shard of p and v, and writes the new p to every rank (multimem.st / peer
  * stores).  `mom` is the local momentum buffer, full length n (only shard r is used when world>1).
  * found_inf (device, may be NULL): when non-NULL and *found_inf != 0 the whole step is skipped.
- * flags: SOD_SGD_ZERO_GRAD zeroes the local gradient buffer on the way out.
+ * flags: SOD_SGD_ZERO_GRAD zeroes the local gradient buffer(s) on the way out.
+ * Mixed precision ("fp32 master" of apex amp, train.py:183): `grad16` (bf16, same flat layout, may be NULL) holds
+ * the gradients autograd produced in bf16 — the kernel adds them to `grad` in registers, so no bf16→fp32 cast
+ * kernel and no fp32 accumulation kernel run per tensor; `shadow16` (bf16, may be NULL) receives the rounded copy
+ * of every updated parameter, which the next forward's convolutions consume directly (no per-iteration weight
+ * cast).  With world>1 the bf16 gradients are folded into the fp32 symmetric buffer by sod_grad_merge_bf16 first,
+ * and `shadow16` is the LOCAL bf16 buffer every rank refreshes from the all-gathered parameters.
  * ------------------------------------------------------------------------------------------------ */
 enum { SOD_SEG_FROZEN = 1 };
 typedef struct {
@@ -110,11 +116,14 @@ enum { SOD_SGD_ZERO_GRAD = 1, SOD_ALGO_NO_MULTIMEM = 2,
        SOD_DEBUG_TIMING = 4 /* syncbn: per-CTA globaltimer stamps behind the workspace (tools/bn_phases.py) */,
        SOD_BN_ACCUMULATE_PARAM_GRADS = 8 /* syncbn_bwd: dgamma/dbeta += (write straight into the bound .grad) */ };
 
-int sod_sgd_momentum(float* param, float* mom, float* grad, int64_t n, const sod_sgd_segment* segs,
-                     int nseg, float inv_scale, const uint32_t* found_inf, int flags, void* stream);
-int sod_allreduce_sgd(const sod_comm* comm, uint64_t grad_off, uint64_t param_off, float* mom, int64_t n,
-                      const sod_sgd_segment* segs, int nseg, float inv_scale, const uint32_t* found_inf,
-                      int flags, void* stream);
+int sod_sgd_momentum(float* param, float* mom, float* grad, void* grad16, void* shadow16, int64_t n,
+                     const sod_sgd_segment* segs, int nseg, float inv_scale, const uint32_t* found_inf, int flags,
+                     void* stream);
+int sod_allreduce_sgd(const sod_comm* comm, uint64_t grad_off, uint64_t param_off, float* mom, void* shadow16,
+                      int64_t n, const sod_sgd_segment* segs, int nseg, float inv_scale,
+                      const uint32_t* found_inf, int flags, void* stream);
+/* grad[i] += float(grad16[i]); grad16[i] = 0   (world>1 pre-pass, one launch over the flat buffers) */
+int sod_grad_merge_bf16(float* grad, void* grad16, int64_t n, void* stream);
 /* *found_inf |= any(!isfinite(grad)) — the amp overflow check (train.py:299), one read of grad */
 int sod_grad_nonfinite(const float* grad, int64_t n, uint32_t* found_inf, void* stream);
 

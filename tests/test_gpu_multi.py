@@ -91,7 +91,7 @@ def _w_allreduce_sgd(rank, world):
         mom = torch.tensor(ve, device="cuda")
         p.copy_(torch.tensor(pe)); g.copy_(torch.tensor(grads[rank]))
         torch.cuda.synchronize(); torch.distributed.barrier()
-        rc = _lib.lib().sod_allreduce_sgd(arena.ref, g_off, p_off, mom.data_ptr(), n, segs, 3, 0.5, None, flags,
+        rc = _lib.lib().sod_allreduce_sgd(arena.ref, g_off, p_off, mom.data_ptr(), None, n, segs, 3, 0.5, None, flags,
                                           torch.cuda.current_stream().cuda_stream)
         assert rc == 0
         torch.cuda.synchronize(); torch.distributed.barrier()

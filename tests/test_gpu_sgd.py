@@ -18,7 +18,7 @@ def _segs(spec):
 
 def _call(p, v, g, spec, inv_scale=1.0, found=None, flags=1):
     from distributed_sod_project_b200 import _lib
-    rc = _lib.lib().sod_sgd_momentum(p.data_ptr(), v.data_ptr(), g.data_ptr(), p.numel(), _segs(spec), len(spec),
+    rc = _lib.lib().sod_sgd_momentum(p.data_ptr(), v.data_ptr(), g.data_ptr(), None, None, p.numel(), _segs(spec), len(spec),
                                      inv_scale, found.data_ptr() if found is not None else None, flags,
                                      torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
