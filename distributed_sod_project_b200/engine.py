@@ -29,8 +29,10 @@ class Trainer:
         self.world = comm.world_size()
         self.channels_last = channels_last
         self.report_items = report_items
+        from . import resample as _resample
         from .network import blocks as _blocks
         _blocks.INTERPOLATE_IN_ACTIVATION_DTYPE = bool(native_interpolate)
+        _resample.ENABLED = bool(native_interpolate)
         init_seed(seed)                                                    # train.py:113
         model = getattr(network, model_name)().to(self.device)            # train.py:141
         if channels_last:

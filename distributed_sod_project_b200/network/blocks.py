@@ -53,17 +53,39 @@ def bilinear(x: torch.Tensor, **kw) -> torch.Tensor:
     """`cus_sample` of the reference (utils/tensor_ops.py:12-18): bilinear, align_corners=False."""
     if len(kw) != 1 or next(iter(kw)) not in ("size", "scale_factor"):
         raise ValueError("bilinear() takes exactly one of size= / scale_factor=")
+    if x.is_cuda:
+        from .. import resample                      # B200 engine: deterministic channels-last ×2 kernel
+        out_hw = kw["size"] if "size" in kw else ((int(x.shape[2] * kw["scale_factor"]), int(x.shape[3] * kw["scale_factor"]))
+                                                  if kw["scale_factor"] == 2 else None)
+        if out_hw is not None:
+            y = resample.upsample2x(x, out_hw)
+            if y is not None:
+                return y
     if INTERPOLATE_IN_ACTIVATION_DTYPE and x.is_cuda and x.dtype != torch.float32 and torch.is_autocast_enabled():
         with torch.autocast("cuda", enabled=False):
             return F.interpolate(x, mode="bilinear", align_corners=False, **kw)
     return F.interpolate(x, mode="bilinear", align_corners=False, **kw)
 
 
+def avgpool2(pool: nn.Module, x: torch.Tensor) -> torch.Tensor:
+    """`h2l_pool` of the reference's SIM (module/MyLightModule.py:14): AvgPool2d((2,2), stride=2)"""
+    if x.is_cuda:
+        from .. import resample
+        y = resample.avgpool2x2(x)
+        if y is not None:
+            return y
+    return pool(x)
+
+
 def upsample_add(*feats: torch.Tensor) -> torch.Tensor:
     """Sum of all inputs resized to the last one's spatial size (utils/tensor_ops.py:21-25)."""
     base = feats[-1]
     for f in feats[:-1]:
-        base = base + bilinear(f, size=base.shape[2:])
+        fused = None
+        if f.is_cuda:
+            from .. import resample
+            fused = resample.upsample2x_add(f, base)       # one kernel: bilinear ×2 of f, plus base
+        base = fused if fused is not None else base + bilinear(f, size=base.shape[2:])
     return base
 
 
@@ -185,7 +207,7 @@ class SIM(nn.Module):
 
     def forward(self, x):
         hw = x.shape[2:]
-        down = self.h2l_pool
+        down = lambda t: avgpool2(self.h2l_pool, t)  # noqa: E731
         # stage 0: split into the two streams
         xh = bn_act(self.bnh_0, self.h2h_0(x))
         xl = bn_act(self.bnl_0, self.h2l_0(down(x)))

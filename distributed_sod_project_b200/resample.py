@@ -1,0 +1,95 @@
+"""Channels-last ×2 bilinear up-sampling (+ fused add) and 2×2 average pooling, backed by csrc/resample.cu.
+
+These are the reference's `cus_sample` / `upsample_add` (utils/tensor_ops.py:12-25) and `h2l_pool`
+(module/MyLightModule.py:14).  The model plugins call `upsample2x` / `upsample2x_add` / `avgpool2x2` through
+`network/blocks.py`; anything the kernels do not cover (CPU tensors, a ratio other than exactly 2, C % 8 != 0)
+returns None so the caller keeps the torch op — those are shapes the TestModel never produces on the hot path.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+ENABLED = False     # switched on by the B200 engine (engine.Trainer)
+
+
+def _ok(x: torch.Tensor) -> bool:
+    return (ENABLED and x.is_cuda and x.dim() == 4 and x.shape[1] % 8 == 0
+            and x.dtype in (torch.bfloat16, torch.float16, torch.float32))
+
+
+def _rows(t: torch.Tensor) -> torch.Tensor:
+    return t if t.is_contiguous(memory_format=torch.channels_last) else t.contiguous(memory_format=torch.channels_last)
+
+
+class _Up2x(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, add):
+        x = _rows(x)
+        n, c, h, w = x.shape
+        if add is not None:
+            add = _rows(add).to(x.dtype)
+        y = torch.empty((n, c, 2 * h, 2 * w), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+        rc = _lib.lib().sod_upsample2x_bilinear_fwd(x.data_ptr(), add.data_ptr() if add is not None else None, y.data_ptr(),
+                                                    n, h, w, c, _lib.dtype_code(x.dtype), _lib.stream_ptr())
+        _lib.check(rc, "sod_upsample2x_bilinear_fwd")
+        _lib.count_launch()
+        ctx.shape = (n, c, h, w)
+        ctx.has_add = add is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        n, c, h, w = ctx.shape
+        dy = _rows(dy)
+        dx = torch.empty((n, c, h, w), dtype=dy.dtype, device=dy.device, memory_format=torch.channels_last)
+        rc = _lib.lib().sod_upsample2x_bilinear_bwd(dy.data_ptr(), dx.data_ptr(), n, h, w, c, _lib.dtype_code(dy.dtype),
+                                                    _lib.stream_ptr())
+        _lib.check(rc, "sod_upsample2x_bilinear_bwd")
+        _lib.count_launch()
+        return dx, (dy if ctx.has_add else None)
+
+
+class _AvgPool2x2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _rows(x)
+        n, c, h, w = x.shape
+        y = torch.empty((n, c, h // 2, w // 2), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+        rc = _lib.lib().sod_avgpool2x2_fwd(x.data_ptr(), y.data_ptr(), n, h // 2, w // 2, c, _lib.dtype_code(x.dtype), _lib.stream_ptr())
+        _lib.check(rc, "sod_avgpool2x2_fwd")
+        _lib.count_launch()
+        ctx.shape = (n, c, h, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        n, c, h, w = ctx.shape
+        dy = _rows(dy)
+        dx = torch.empty((n, c, h, w), dtype=dy.dtype, device=dy.device, memory_format=torch.channels_last)
+        rc = _lib.lib().sod_avgpool2x2_bwd(dy.data_ptr(), dx.data_ptr(), n, h // 2, w // 2, c, _lib.dtype_code(dy.dtype), _lib.stream_ptr())
+        _lib.check(rc, "sod_avgpool2x2_bwd")
+        _lib.count_launch()
+        return dx
+
+
+def upsample2x(x: torch.Tensor, out_hw) -> torch.Tensor | None:
+    """bilinear to `out_hw` if that is exactly twice the input size, else None (caller falls back to F.interpolate)"""
+    if not _ok(x) or tuple(out_hw) != (2 * x.shape[2], 2 * x.shape[3]):
+        return None
+    return _Up2x.apply(x, None)
+
+
+def upsample2x_add(coarse: torch.Tensor, lateral: torch.Tensor) -> torch.Tensor | None:
+    """lateral + bilinear(coarse → lateral's size), one kernel; None if not exactly ×2"""
+    if not _ok(coarse) or tuple(lateral.shape[2:]) != (2 * coarse.shape[2], 2 * coarse.shape[3]) \
+            or lateral.shape[:2] != coarse.shape[:2] or lateral.dtype != coarse.dtype:
+        return None
+    return _Up2x.apply(coarse, lateral)
+
+
+def avgpool2x2(x: torch.Tensor) -> torch.Tensor | None:
+    if not _ok(x) or x.shape[2] % 2 or x.shape[3] % 2:
+        return None
+    return _AvgPool2x2.apply(x)

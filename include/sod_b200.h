@@ -164,6 +164,19 @@ int sod_syncbn_bwd(const void* dy, const void* x, const void* pre_add, const voi
                    uint64_t stats_off, uint32_t seq, const uint32_t* epoch, void* workspace, size_t workspace_bytes,
                    int flags, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Resampling ops on either side of the SyncBN kernels, channels-last [N,H,W,C], C % 8 == 0.
+ * sod_upsample2x_bilinear_*: bilinear ×2, align_corners=False — `cus_sample` / `upsample_add`
+ *   (utils/tensor_ops.py:12-25; call sites network/TestModel.py:100-126, module/MyLightModule.py:42-52);
+ *   `add` (may be NULL) is the tensor `upsample_add` sums with, already at the output size.  (h, w) = INPUT size.
+ *   The backward is a gather (no atomics): deterministic.
+ * sod_avgpool2x2_*: AvgPool2d((2,2), stride=2) — `h2l_pool` (module/MyLightModule.py:14); (h_out, w_out) = OUTPUT size.
+ * ------------------------------------------------------------------------------------------------ */
+int sod_upsample2x_bilinear_fwd(const void* x, const void* add, void* y, int n, int h, int w, int c, int dtype, void* stream);
+int sod_upsample2x_bilinear_bwd(const void* dy, void* dx, int n, int h, int w, int c, int dtype, void* stream);
+int sod_avgpool2x2_fwd(const void* x, void* y, int n, int h_out, int w_out, int c, int dtype, void* stream);
+int sod_avgpool2x2_bwd(const void* dy, void* dx, int n, int h_out, int w_out, int c, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

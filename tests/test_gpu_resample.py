@@ -1,0 +1,76 @@
+"""Channels-last ×2 bilinear (+fused add) and 2×2 average-pool kernels against torch's own ops (fwd and bwd)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _enable():
+    from distributed_sod_project_b200 import resample
+    old, resample.ENABLED = resample.ENABLED, True
+    yield
+    resample.ENABLED = old
+
+
+def _mk(shape, dtype, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(shape, generator=g).to(dtype).cuda().contiguous(memory_format=torch.channels_last)
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 5, 7), (16, 64, 10, 10), (3, 8, 1, 1), (2, 64, 40, 40), (1, 128, 2, 9)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("with_add", [False, True])
+def test_upsample2x_matches_interpolate(shape, dtype, with_add):
+    from distributed_sod_project_b200 import resample
+    n, c, h, w = shape
+    x1 = _mk(shape, dtype, 1).requires_grad_(True)
+    x2 = x1.detach().clone().requires_grad_(True)
+    lat1 = _mk((n, c, 2 * h, 2 * w), dtype, 2).requires_grad_(True) if with_add else None
+    lat2 = lat1.detach().clone().requires_grad_(True) if with_add else None
+    y1 = resample.upsample2x_add(x1, lat1) if with_add else resample.upsample2x(x1, (2 * h, 2 * w))
+    assert y1 is not None and y1.is_contiguous(memory_format=torch.channels_last)
+    ref = F.interpolate(x2.float(), size=(2 * h, 2 * w), mode="bilinear", align_corners=False)
+    if with_add:
+        ref = ref + lat2.float()
+    tol = dict(rtol=1e-5, atol=1e-5) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-2)
+    assert torch.allclose(y1.float(), ref, **tol)
+    dy = _mk((n, c, 2 * h, 2 * w), dtype, 3)
+    y1.backward(dy)
+    ref.backward(dy.float())
+    assert torch.allclose(x1.grad.float(), x2.grad.float(), **(dict(rtol=1e-5, atol=1e-5) if dtype == torch.float32 else dict(rtol=3e-2, atol=3e-2)))
+    if with_add:
+        assert torch.equal(lat1.grad, dy)
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 6, 8), (16, 64, 20, 20), (1, 8, 2, 2)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_avgpool2x2_matches_torch(shape, dtype):
+    from distributed_sod_project_b200 import resample
+    x1 = _mk(shape, dtype, 5).requires_grad_(True)
+    x2 = x1.detach().clone().requires_grad_(True)
+    y1 = resample.avgpool2x2(x1)
+    ref = F.avg_pool2d(x2.float(), 2, 2)
+    tol = dict(rtol=1e-6, atol=1e-6) if dtype == torch.float32 else dict(rtol=1e-2, atol=1e-2)
+    assert torch.allclose(y1.float(), ref, **tol)
+    dy = _mk(tuple(ref.shape), dtype, 6)
+    y1.backward(dy)
+    ref.backward(dy.float())
+    assert torch.allclose(x1.grad.float(), x2.grad.float(), **tol)
+
+
+def test_unsupported_shapes_fall_back_and_backward_is_deterministic():
+    from distributed_sod_project_b200 import resample
+    x = _mk((2, 32, 5, 7), torch.bfloat16, 1)
+    assert resample.upsample2x(x, (11, 14)) is None            # not exactly ×2
+    assert resample.avgpool2x2(_mk((1, 32, 5, 6), torch.float32, 2)) is None   # odd height
+    assert resample.upsample2x(torch.zeros(1, 8, 2, 2), (4, 4)) is None        # CPU
+    xs = _mk((4, 64, 20, 20), torch.bfloat16, 3).requires_grad_(True)
+    dy = _mk((4, 64, 40, 40), torch.bfloat16, 4)
+    grads = []
+    for _ in range(3):
+        xs.grad = None
+        resample.upsample2x(xs, (40, 40)).backward(dy)
+        grads.append(xs.grad.clone())
+    assert torch.equal(grads[0], grads[1]) and torch.equal(grads[0], grads[2])
