@@ -57,16 +57,17 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs"""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms; started before warm-up so that it is already
+    streaming when the (possibly sub-second) timed region runs; `mark()` brackets the timed region."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.t0, self.t1 = [], None, index, None, None
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -76,10 +77,17 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark(self):
+        if self.t0 is None:
+            self.t0 = time.time()
+        else:
+            self.t1 = time.time()
 
     def __exit__(self, *a):
         if self.proc:
+            time.sleep(0.25)            # let the last in-window sample arrive
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
@@ -87,8 +95,12 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
+        t0, t1 = self.t0 or 0.0, self.t1 or float("inf")
+        inside = [r for t, r in self.rows if t0 <= t <= t1 + 0.15]
+        if not inside and self.rows:     # region shorter than the sampling period: the samples that bracket it
+            inside = [r for t, r in self.rows if t0 - 0.3 <= t <= t1 + 0.3] or [self.rows[-1][1]]
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in inside:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
             except (ValueError, IndexError):
@@ -297,6 +309,7 @@ def run_b200_arm(args):
         return float(ms.item())
 
     # -- device-resident arm ---------------------------------------------------------------------------
+    clk = ClockSampler(local).__enter__()
     syncbn.TRACE = []
     for i in range(args.warmup):
         tr.forward_backward_update(*dev[i % nb])
@@ -313,9 +326,11 @@ def run_b200_arm(args):
         with open(os.environ["SOD_BENCH_PROFILE"], "w") as f:
             f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90))
     rid = torch.cuda.nvtx.range_start("timed")      # start/end range: process-wide (backward runs on autograd's thread)
-    with ClockSampler(local) as clk:
-        ms = timed(lambda i: tr.forward_backward_update(*dev[i % nb]), args.steps)
+    clk.mark()
+    ms = timed(lambda i: tr.forward_backward_update(*dev[i % nb]), args.steps)
+    clk.mark()
     torch.cuda.nvtx.range_end(rid)
+    clk.__exit__()
     launches = _lib.launches - l0
     log(f'timed region done: {ms / args.steps:.2f} ms/step')
     value = world * BS * args.steps / (ms * 1e-3)
@@ -389,7 +404,8 @@ def run_sweep(args):
         ref = torch.empty(n, device="cuda")
         res = {"bytes": nbytes}
         for name, fn in (("nccl", lambda: dist.all_reduce(ref)),
-                         ("sod_multimem" if arena.has_multicast else "sod_p2p", lambda: arena.allreduce_(off, n, algo=2)),
+                         ("sod_multimem" if arena.has_multicast else "sod_p2p", lambda: arena.allreduce_(off, n, algo=2, force_multimem=True)),
+                         ("sod_auto", lambda: arena.allreduce_(off, n, algo=0)),
                          ("sod_p2p_forced", lambda: arena.allreduce_(off, n, algo=2, no_multimem=True)),
                          ("sod_one_shot", (lambda: arena.allreduce_(off, n, algo=1)) if nbytes <= (1 << 20) else None)):
             if fn is None:

@@ -18,6 +18,7 @@ SOD_SEG_FROZEN = 1
 SOD_SGD_ZERO_GRAD = 1
 SOD_ALGO_NO_MULTIMEM = 2
 SOD_BN_ACCUMULATE_PARAM_GRADS = 8
+SOD_ALGO_FORCE_MULTIMEM = 16
 
 
 class SodError(RuntimeError):

@@ -88,9 +88,10 @@ class Arena:
             raise _lib.SodError(f"device-side barrier timeout (flag 0x{v & 0xffffffff:08x}): a peer rank is not making progress")
 
     # -- plain all-reduce (sweep, scalar mean) -----------------------------------------------------------
-    def allreduce_(self, offset: int, numel: int, scale: float = 1.0, algo: int = 0, no_multimem: bool = False):
-        rc = _lib.lib().sod_allreduce_f32(self.ref, offset, numel, float(scale), int(algo),
-                                          _lib.SOD_ALGO_NO_MULTIMEM if no_multimem else 0, _lib.stream_ptr())
+    def allreduce_(self, offset: int, numel: int, scale: float = 1.0, algo: int = 0, no_multimem: bool = False,
+                   force_multimem: bool = False):
+        flags = (_lib.SOD_ALGO_NO_MULTIMEM if no_multimem else 0) | (_lib.SOD_ALGO_FORCE_MULTIMEM if force_multimem else 0)
+        rc = _lib.lib().sod_allreduce_f32(self.ref, offset, numel, float(scale), int(algo), flags, _lib.stream_ptr())
         _lib.check(rc, "sod_allreduce_f32")
         _lib.count_launch()
 

@@ -368,7 +368,9 @@ extern "C" int sod_allreduce_sgd(const sod_comm* comm, uint64_t grad_off, uint64
     const unsigned grid = comm_grid((nvec + c.world - 1) / c.world);
     const float scale = inv_scale / static_cast<float>(c.world);
     const int zg = (flags & SOD_SGD_ZERO_GRAD) ? 1 : 0;
-    const bool mc = (c.mc != 0) && !(flags & SOD_ALGO_NO_MULTIMEM);
+    // measured (profiles/r01_allreduce_sweep_w2.json): with two ranks the in-switch reduction loses to plain peer loads
+    // (288 vs 175 µs at 99.6 MB); from four ranks up NVLS wins (281 vs 346 µs at eight)
+    const bool mc = (c.mc != 0) && !(flags & SOD_ALGO_NO_MULTIMEM) && (c.world > 2 || (flags & SOD_ALGO_FORCE_MULTIMEM));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (mc)
         allreduce_sgd_kernel<true><<<grid, kThreads, 0, s>>>(c, grad_off, param_off, reinterpret_cast<float4*>(mom), nvec, t,
@@ -399,7 +401,9 @@ extern "C" int sod_allreduce_f32(const sod_comm* comm, uint64_t off, int64_t n, 
         allreduce_one_shot_kernel<<<grid, kThreads, 0, s>>>(c, off, nvec, scale);
     } else {
         const unsigned grid = comm_grid((nvec + c.world - 1) / c.world);
-        const bool mc = (c.mc != 0) && !(flags & SOD_ALGO_NO_MULTIMEM);
+        // measured (profiles/r01_allreduce_sweep_w2.json): with two ranks the in-switch reduction loses to plain peer loads
+    // (288 vs 175 µs at 99.6 MB); from four ranks up NVLS wins (281 vs 346 µs at eight)
+    const bool mc = (c.mc != 0) && !(flags & SOD_ALGO_NO_MULTIMEM) && (c.world > 2 || (flags & SOD_ALGO_FORCE_MULTIMEM));
         if (mc) allreduce_two_shot_kernel<true><<<grid, kThreads, 0, s>>>(c, off, nvec, scale);
         else allreduce_two_shot_kernel<false><<<grid, kThreads, 0, s>>>(c, off, nvec, scale);
     }

@@ -114,7 +114,8 @@ typedef struct {
 } sod_sgd_segment;
 enum { SOD_SGD_ZERO_GRAD = 1, SOD_ALGO_NO_MULTIMEM = 2,
        SOD_DEBUG_TIMING = 4 /* syncbn: per-CTA globaltimer stamps behind the workspace (tools/bn_phases.py) */,
-       SOD_BN_ACCUMULATE_PARAM_GRADS = 8 /* syncbn_bwd: dgamma/dbeta += (write straight into the bound .grad) */ };
+       SOD_BN_ACCUMULATE_PARAM_GRADS = 8 /* syncbn_bwd: dgamma/dbeta += (write straight into the bound .grad) */,
+       SOD_ALGO_FORCE_MULTIMEM = 16 /* use NVLS even at world 2, where the default is peer loads */ };
 
 int sod_sgd_momentum(float* param, float* mom, float* grad, void* grad16, void* shadow16, int64_t n,
                      const sod_sgd_segment* segs, int nseg, float inv_scale, const uint32_t* found_inf, int flags,

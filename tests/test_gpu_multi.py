@@ -47,7 +47,7 @@ def _w_allreduce(rank, world):
     arena = comm.Arena(payload_bytes=(64 << 20) + 4096)
     off = arena.alloc(64 << 20)
     for n in (4, 1024, 65536 + 4, 1 << 20, (16 << 20) // 4 + 8):
-        for algo, nomc in ((2, False), (2, True), (1, False)):
+        for algo, nomc in ((2, False), (2, True), (1, False), (0, False)):
             if algo == 1 and n * 4 > (1 << 20):
                 continue
             buf = arena.view(off, n, torch.float32)
