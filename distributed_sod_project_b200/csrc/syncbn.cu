@@ -38,7 +38,8 @@ constexpr int kMaxC = 2048;
 constexpr int kMaxStages = 16;
 constexpr int kMaxStreams = 4;
 constexpr int kMaxGrid = 160;
-constexpr int kSmemFixed = 256 /*barriers*/ + 32768 /*red*/ + 3 * kMaxC * 4 /*coefficients*/;
+constexpr int kRedBytes = 49152;          // scratch of the CTA reduction: kWarps x 24 statistics x 32 lanes x 4 B
+constexpr int kSmemFixed = 256 /*barriers*/ + kRedBytes + 3 * kMaxC * 4 /*coefficients*/;
 
 struct BnGeom {
     int C, es, L;                // channels, element bytes, lanes (= C/8 packets per row)
@@ -50,8 +51,9 @@ struct BnGeom {
 };
 
 struct BnWork {
-    uint2* partials;   // [strips][2C] packets
+    uint2* partials;   // [strips][2C or 3C] packets
     uint2* ll_local;   // [2C] packets, exchange slot when world == 1
+    uint2* locpk;      // [3C] packets: GPU-local totals handed from the slice owners to CTA 0 (conv-bias gradient)
     unsigned long long* stamps;  // [kMaxGrid][4] globaltimer ns when SOD_DEBUG_TIMING is set, else null
 };
 
@@ -69,6 +71,8 @@ struct BnFwd {
     const float *gamma, *beta;
     float *rmean, *rvar, *smean, *sinvstd;
     long long* nbt;  // num_batches_tracked (+= 1) or null
+    const void *cbias1, *cbias2;  // biases of the convolution(s) feeding this BN, folded in here (z = x + pre + b1 + b2)
+    int cbias_dtype;
     float momentum, eps;
     int relu, training;
     BnGeom g;
@@ -85,6 +89,9 @@ struct BnBwd {
     void *dz, *dres;
     const float *gamma, *smean, *sinvstd;
     float *dgamma, *dbeta;
+    const void *cbias1, *cbias2;
+    void *dcbias1, *dcbias2;      // += Σ_rows dz (gradient of a folded conv bias), dtype cbias_dtype
+    int cbias_dtype;
     int relu, accumulate;
     BnGeom g;
     BnWork w;
@@ -94,6 +101,25 @@ struct BnBwd {
     const uint32_t* epoch;
     int use_mc;
 };
+
+// folded conv bias of the 8 channels a thread owns (fp32 master or bf16 shadow leaves)
+__device__ __forceinline__ float ld_bias(const void* p, int dtype, int ch) {
+    if (p == nullptr) return 0.f;
+    if (dtype == SOD_F32) return static_cast<const float*>(p)[ch];
+    if (dtype == SOD_BF16) return __bfloat162float(static_cast<const __nv_bfloat16*>(p)[ch]);
+    return __half2float(static_cast<const __half*>(p)[ch]);
+}
+__device__ __forceinline__ void acc_bias_grad(void* p, int dtype, int ch, float v) {
+    if (p == nullptr) return;
+    if (dtype == SOD_F32) static_cast<float*>(p)[ch] += v;
+    else if (dtype == SOD_BF16) {
+        __nv_bfloat16* q = static_cast<__nv_bfloat16*>(p) + ch;
+        *q = __float2bfloat16_rn(__bfloat162float(*q) + v);
+    } else {
+        __half* q = static_cast<__half*>(p) + ch;
+        *q = __float2half_rn(__half2float(*q) + v);
+    }
+}
 
 // tag of this call: host counter (eager) or device epoch + call index (CUDA-graph replay)
 __device__ __forceinline__ uint32_t call_tag(uint32_t seq, const uint32_t* epoch) {
@@ -220,45 +246,55 @@ __device__ __forceinline__ void issue_chunk(Ring& ring, const BnGeom& g, const v
         if (src[k] != nullptr) bulk_g2s(ring.buf(s, k), static_cast<const char*>(src[k]) + off, bytes, &ring.full[s]);
 }
 
-// ---- CTA-level reduction of 16 per-thread accumulators over the threads that share a lane -----------------
-// on return `red[j]`, j = k*L + l  (k<8: first statistic of channel l*8+k, k>=8: second statistic), holds the CTA total
-__device__ __forceinline__ void cta_reduce16(float (&a)[16], int L, float* red /*[8192]*/) {
+// ---- CTA-level reduction of NA (16 or 24) per-thread accumulators over the threads that share a lane ----------
+// on return `red[j]`, j = k*L + l  (statistic k of channel group l), holds the CTA total
+template <int NA>
+__device__ __forceinline__ void cta_reduce(float (&a)[NA], int L, float* red /*[kRedBytes/4]*/) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n16 = 16 * L;
+    const int nent = NA * L;
     if (L <= 32) {
         // threads with equal (lane % L) inside a warp share a channel group: butterfly over the row-lanes
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
+        for (int k = 0; k < NA; ++k) {
             float v = a[k];
             for (int o = 16; o >= L; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
             a[k] = v;
         }
         if (lane < L) {
 #pragma unroll
-            for (int k = 0; k < 16; ++k) red[warp * n16 + k * L + lane] = a[k];
+            for (int k = 0; k < NA; ++k) red[warp * nent + k * L + lane] = a[k];
         }
         cbar();
-        float tot = 0.f;
-        if (tid < n16) {
+        float tot[2] = {0.f, 0.f};
 #pragma unroll
-            for (int w = 0; w < kWarps; ++w) tot += red[w * n16 + tid];
+        for (int h = 0; h < 2; ++h) {
+            const int j = tid + h * kThreads;
+            if (j < nent) {
+#pragma unroll
+                for (int w = 0; w < kWarps; ++w) tot[h] += red[w * nent + j];
+            }
         }
         cbar();
-        if (tid < n16) red[tid] = tot;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int j = tid + h * kThreads;
+            if (j < nent) red[j] = tot[h];
+        }
     } else {
-        // L in {64,128,256}: thread tid owns lane l = tid % L; R = kThreads / L threads share it
+        // L in {64,128,256}: thread tid owns lane l = tid % L; R = kThreads / L threads share it.
+        // rounds of 8 statistics; scratch [R][8][L] floats = 16 KB sits behind the NA*L results
         const int l = tid % L, r = tid / L, R = kThreads / L;
-        // two rounds of 8 statistics so that the scratch stays within 32 KB: [R][8][L] floats = 16 KB
+        float* scratch = red + NA * 256;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        for (int part = 0; part < NA / 8; ++part) {
             cbar();
 #pragma unroll
-            for (int k = 0; k < 8; ++k) red[4096 + (r * 8 + k) * L + l] = a[half * 8 + k];
+            for (int k = 0; k < 8; ++k) scratch[(r * 8 + k) * L + l] = a[part * 8 + k];
             cbar();
             for (int j = tid; j < 8 * L; j += kThreads) {
                 float tot = 0.f;
-                for (int rr = 0; rr < R; ++rr) tot += red[4096 + rr * 8 * L + j];
-                red[half * 8 * L + j] = tot;  // j = k*L + l
+                for (int rr = 0; rr < R; ++rr) tot += scratch[rr * 8 * L + j];
+                red[part * 8 * L + j] = tot;  // j = k*L + l
             }
         }
     }
@@ -268,9 +304,12 @@ __device__ __forceinline__ void cta_reduce16(float (&a)[16], int L, float* red /
 // hop 1 + hop 2 (+ optional per-entry side effect through `on_total`), then collect into red[0..n16)
 template <typename F>
 __device__ __forceinline__ void exchange(const BnGeom& g, const BnWork& w, const CommDev& c, int use_mc, uint64_t stats_off,
-                                         uint32_t tag, float* red, int* s_fail, F on_total) {
+                                         uint32_t tag, float* red, int* s_fail, int na, F on_total) {
+    // `na` statistics per channel group enter the CTA → GPU reduction (hop 1); only the first 16 are exchanged between
+    // GPUs (hop 2).  With na == 24 the GPU-local totals of statistics 0-7 and 16-23 are also left in w.locpk for CTA 0.
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n16 = 16 * g.L;
+    const int nglob = 16 * g.L;
+    const int n16 = na * g.L;
     const int strips = static_cast<int>(gridDim.x);
     const unsigned long long timeout = c.timeout_cycles ? c.timeout_cycles : 4000000000ull;
     int fail = 0;
@@ -302,12 +341,15 @@ __device__ __forceinline__ void exchange(const BnGeom& g, const BnWork& w, const
         }
         acc = warp_sum(acc);
         if (lane == 0) {
-            on_total(j, acc);
-            publish(c, use_mc, stats_off, w.ll_local, g.C, j, acc, tag);  // hop 2
+            if (j < nglob) {
+                on_total(j, acc);
+                publish(c, use_mc, stats_off, w.ll_local, g.C, j, acc, tag);  // hop 2
+            }
+            if (na > 16) st_packet_gpu(w.locpk + j, acc, tag);
         }
     }
     cbar();  // everyone has finished reading red[] (hop 1a) before it is overwritten
-    for (int j = tid; j < n16; j += kThreads) red[j] = collect(c, stats_off, w.ll_local, g.C, j, tag, timeout, fail);
+    for (int j = tid; j < nglob; j += kThreads) red[j] = collect(c, stats_off, w.ll_local, g.C, j, tag, timeout, fail);
     if (fail) {
         *s_fail = 1;
         if (c.error_flag) atomicExch(c.error_flag, 0xDEAD0001u);
@@ -358,7 +400,7 @@ template <typename T, int PPT, bool RES>
 __global__ void __launch_bounds__(kBlock, 1) syncbn_fwd_kernel(const __grid_constant__ BnFwd prm) {
     extern __shared__ __align__(128) unsigned char smem[];
     float* red = reinterpret_cast<float*>(smem + 256);
-    float* s_scale = reinterpret_cast<float*>(smem + 256 + 32768);
+    float* s_scale = reinterpret_cast<float*>(smem + 256 + kRedBytes);
     float* s_shift = s_scale + kMaxC;
     __shared__ int s_fail;
 
@@ -384,6 +426,11 @@ __global__ void __launch_bounds__(kBlock, 1) syncbn_fwd_kernel(const __grid_cons
 
     // ---- consumers -------------------------------------------------------------------------------------
     const int l = tid % L;
+    const bool has_cb = prm.cbias1 != nullptr || prm.cbias2 != nullptr;
+    float cb[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        cb[k] = ld_bias(prm.cbias1, prm.cbias_dtype, l * 8 + k) + ld_bias(prm.cbias2, prm.cbias_dtype, l * 8 + k);
     const T* __restrict__ gres = RES ? static_cast<const T*>(prm.res) : nullptr;
     T* __restrict__ gy = static_cast<T*>(prm.y);
     // affine / running parameters are fetched now so their DRAM latency hides behind phase 1
@@ -426,6 +473,10 @@ __global__ void __launch_bounds__(kBlock, 1) syncbn_fwd_kernel(const __grid_cons
 #pragma unroll
                             for (int k = 0; k < 8; ++k) z[k] += t[k];
                         }
+                        if (has_cb) {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) z[k] += cb[k];
+                        }
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
                             a[k] += z[k];
@@ -437,8 +488,8 @@ __global__ void __launch_bounds__(kBlock, 1) syncbn_fwd_kernel(const __grid_cons
             if (i + NS < sp.n) ring.release(s);  // recycled within phase 1
         }
         stamp(prm.w, 1);
-        cta_reduce16(a, L, red);
-        exchange(g, prm.w, prm.c, prm.use_mc, prm.stats_off, call_tag(prm.tag, prm.epoch), red, &s_fail, [](int, float) {});
+        cta_reduce<16>(a, L, red);
+        exchange(g, prm.w, prm.c, prm.use_mc, prm.stats_off, call_tag(prm.tag, prm.epoch), red, &s_fail, 16, [](int, float) {});
         stamp(prm.w, 2);
         // ---- per-channel coefficients --------------------------------------------------------------------
         const float n = static_cast<float>(g.rows) * static_cast<float>(prm.c.world);
@@ -476,7 +527,7 @@ __global__ void __launch_bounds__(kBlock, 1) syncbn_fwd_kernel(const __grid_cons
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         sc[k] = s_scale[l * 8 + k];
-        sh[k] = s_shift[l * 8 + k];
+        sh[k] = fmaf(cb[k], sc[k], s_shift[l * 8 + k]);     // (z + b)*sc + sh  ==  z*sc + (b*sc + sh)
     }
     const bool relu = prm.relu != 0;
     const int nresident = training ? sp.n - nres0 : 0;
@@ -562,11 +613,11 @@ __global__ void __launch_bounds__(kBlock, 1) syncbn_fwd_kernel(const __grid_cons
 // =================================================================================================
 // backward
 // =================================================================================================
-template <typename T>
+template <typename T, int NSTAT>
 __global__ void __launch_bounds__(kBlock, 1) syncbn_bwd_kernel(const __grid_constant__ BnBwd prm) {
     extern __shared__ __align__(128) unsigned char smem[];
     float* red = reinterpret_cast<float*>(smem + 256);
-    float* s_a = reinterpret_cast<float*>(smem + 256 + 32768);
+    float* s_a = reinterpret_cast<float*>(smem + 256 + kRedBytes);
     float* s_b = s_a + kMaxC;
     float* s_d = s_b + kMaxC;
     __shared__ int s_fail;
@@ -609,6 +660,14 @@ __global__ void __launch_bounds__(kBlock, 1) syncbn_bwd_kernel(const __grid_cons
     float mean[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) mean[k] = s_d[l * 8 + k];
+    // folded conv bias: z = x + pre + b, so (z - mean) = (x + pre) - (mean - b): fold b into the per-thread mean
+    constexpr bool kFold = NSTAT == 24;
+    float cb[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        cb[k] = kFold ? ld_bias(prm.cbias1, prm.cbias_dtype, l * 8 + k) + ld_bias(prm.cbias2, prm.cbias_dtype, l * 8 + k) : 0.f;
+        mean[k] -= cb[k];
+    }
 
     // one packet of work, shared by both phases (measured: interleaving two packets per thread only added register
     // pressure here — four streams per packet already give the scheduler independent loads)
@@ -630,9 +689,9 @@ __global__ void __launch_bounds__(kBlock, 1) syncbn_bwd_kernel(const __grid_cons
     };
 
     // ---- phase 1: Σ dy_m and Σ dy_m (z - mean) -------------------------------------------------------------
-    float a[16];
+    float a[NSTAT];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) a[k] = 0.f;
+    for (int k = 0; k < NSTAT; ++k) a[k] = 0.f;
     for (int i = 0; i < sp.n; ++i) {
         const int s = i % NS;
         ring.wait_full(s);
@@ -642,14 +701,16 @@ __global__ void __launch_bounds__(kBlock, 1) syncbn_bwd_kernel(const __grid_cons
             load_packet(s, q, d, z);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
+                const float zc = z[k] - mean[k];
                 a[k] += d[k];
-                a[8 + k] = fmaf(d[k], z[k] - mean[k], a[8 + k]);
+                a[8 + k] = fmaf(d[k], zc, a[8 + k]);
+                if (kFold) a[16 + k] += zc;          // Σ (z - mean) over the LOCAL rows → gradient of the folded bias
             }
         }
         if (i + NS < sp.n) ring.release(s);
     }
     stamp(prm.w, 1);
-    cta_reduce16(a, L, red);
+    cta_reduce<NSTAT>(a, L, red);
     {
         const float* sinv = s_b;
         float* dgamma = prm.dgamma;
@@ -657,7 +718,7 @@ __global__ void __launch_bounds__(kBlock, 1) syncbn_bwd_kernel(const __grid_cons
         const int LL = L;
         const bool accumulate = prm.accumulate != 0;
         // GPU-local totals are also the local parameter gradients (the gradient all-reduce averages them later)
-        exchange(g, prm.w, prm.c, prm.use_mc, prm.stats_off, call_tag(prm.tag, prm.epoch), red, &s_fail, [=](int j, float tot) {
+        exchange(g, prm.w, prm.c, prm.use_mc, prm.stats_off, call_tag(prm.tag, prm.epoch), red, &s_fail, NSTAT, [=](int j, float tot) {
             const int k = j / LL, ll = j % LL;
             const int ch = ll * 8 + (k & 7);
             if (accumulate) {
@@ -679,7 +740,22 @@ __global__ void __launch_bounds__(kBlock, 1) syncbn_bwd_kernel(const __grid_cons
             const float invstd = s_b[ch];
             const float A = s_a[ch] * invstd;
             const float B = -A * invstd * invstd * mean_dy_xmu;
-            const float mu = s_d[ch];
+            float mu = s_d[ch];
+            if (kFold) {
+                mu -= ld_bias(prm.cbias1, prm.cbias_dtype, ch) + ld_bias(prm.cbias2, prm.cbias_dtype, ch);
+                if (blockIdx.x == 0) {
+                    // Σ_local dz = A (Σ_loc dy_m - n_loc mean_dy) + B Σ_loc (z - mean): the GPU-local totals come from the
+                    // slice owners as packets (same tag), so no fence or barrier is involved
+                    int fail = 0;
+                    const unsigned long long to = prm.c.timeout_cycles ? prm.c.timeout_cycles : 4000000000ull;
+                    const float s1 = wait_packet_gpu(prm.w.locpk + (k * L + ll), call_tag(prm.tag, prm.epoch), to, fail);
+                    const float s3 = wait_packet_gpu(prm.w.locpk + ((16 + k) * L + ll), call_tag(prm.tag, prm.epoch), to, fail);
+                    const float db = A * (s1 - static_cast<float>(g.rows) * mean_dy) + B * s3;
+                    acc_bias_grad(prm.dcbias1, prm.cbias_dtype, ch, db);
+                    acc_bias_grad(prm.dcbias2, prm.cbias_dtype, ch, db);
+                    if (fail && prm.c.error_flag) atomicExch(prm.c.error_flag, 0xDEAD0003u);
+                }
+            }
             s_a[ch] = A;
             s_b[ch] = B;
             s_d[ch] = -A * mean_dy - B * mu;
@@ -763,8 +839,10 @@ static size_t bn_ws_layout(int C, BnWork* w, void* base) {
     size_t off = 0;
     if (w) w->ll_local = reinterpret_cast<uint2*>(static_cast<char*>(base) + off);
     off += static_cast<size_t>(2) * kMaxC * sizeof(uint2);
+    if (w) w->locpk = reinterpret_cast<uint2*>(static_cast<char*>(base) + off);
+    off += static_cast<size_t>(3) * kMaxC * sizeof(uint2);
     if (w) w->partials = reinterpret_cast<uint2*>(static_cast<char*>(base) + off);
-    off += static_cast<size_t>(kMaxGrid) * 2 * C * sizeof(uint2);
+    off += static_cast<size_t>(kMaxGrid) * 3 * C * sizeof(uint2);
     if (w) w->stamps = nullptr;
     return off;
 }
@@ -803,8 +881,9 @@ extern "C" int sod_syncbn_fwd(const void* x, const void* pre_add, const void* re
                               const float* gamma, const float* beta, float* running_mean, float* running_var,
                               float* save_mean, float* save_invstd, int64_t rows, int channels, float momentum,
                               float eps, int relu, int training, const sod_comm* comm, uint64_t stats_off,
-                              uint32_t seq, const uint32_t* epoch, int64_t* num_batches_tracked, void* workspace,
-                              size_t workspace_bytes, int flags, void* stream) {
+                              uint32_t seq, const uint32_t* epoch, int64_t* num_batches_tracked, const void* conv_bias1,
+                              const void* conv_bias2, int conv_bias_dtype, void* workspace, size_t workspace_bytes,
+                              int flags, void* stream) {
     using namespace sod;
     SOD_CHECK_ARG(x && y && gamma && beta && workspace, SOD_EINVAL);
     SOD_CHECK_ARG(training ? (save_mean && save_invstd) : (running_mean && running_var), SOD_EINVAL);
@@ -829,6 +908,7 @@ extern "C" int sod_syncbn_fwd(const void* x, const void* pre_add, const void* re
     p.gamma = gamma; p.beta = beta; p.rmean = running_mean; p.rvar = running_var;
     p.smean = save_mean; p.sinvstd = save_invstd;
     p.nbt = training ? reinterpret_cast<long long*>(num_batches_tracked) : nullptr;
+    p.cbias1 = conv_bias1; p.cbias2 = conv_bias2; p.cbias_dtype = conv_bias_dtype;
     p.momentum = momentum; p.eps = eps; p.relu = relu; p.training = training;
     p.stats_off = stats_off; p.tag = seq; p.epoch = epoch;
     p.use_mc = (p.c.mc != 0) && !(flags & SOD_ALGO_NO_MULTIMEM);
@@ -849,8 +929,9 @@ extern "C" int sod_syncbn_fwd(const void* x, const void* pre_add, const void* re
 extern "C" int sod_syncbn_bwd(const void* dy, const void* x, const void* pre_add, const void* y, void* dz, void* dres,
                               int dtype, const float* gamma, const float* save_mean, const float* save_invstd,
                               float* dgamma, float* dbeta, int64_t rows, int channels, int relu, const sod_comm* comm,
-                              uint64_t stats_off, uint32_t seq, const uint32_t* epoch, void* workspace,
-                              size_t workspace_bytes, int flags, void* stream) {
+                              uint64_t stats_off, uint32_t seq, const uint32_t* epoch, const void* conv_bias1,
+                              const void* conv_bias2, void* dconv_bias1, void* dconv_bias2, int conv_bias_dtype,
+                              void* workspace, size_t workspace_bytes, int flags, void* stream) {
     using namespace sod;
     SOD_CHECK_ARG(dy && x && dz && gamma && save_mean && save_invstd && dgamma && dbeta && workspace, SOD_EINVAL);
     SOD_CHECK_ARG(!relu || y, SOD_EINVAL);
@@ -873,9 +954,13 @@ extern "C" int sod_syncbn_bwd(const void* dy, const void* x, const void* pre_add
     p.gamma = gamma; p.smean = save_mean; p.sinvstd = save_invstd; p.dgamma = dgamma; p.dbeta = dbeta;
     p.relu = relu; p.stats_off = stats_off; p.tag = seq; p.epoch = epoch;
     p.accumulate = (flags & SOD_BN_ACCUMULATE_PARAM_GRADS) ? 1 : 0;
+    p.cbias1 = conv_bias1; p.cbias2 = conv_bias2; p.dcbias1 = dconv_bias1; p.dcbias2 = dconv_bias2; p.cbias_dtype = conv_bias_dtype;
+    const bool fold = conv_bias1 != nullptr || conv_bias2 != nullptr;
     p.use_mc = (p.c.mc != 0) && !(flags & SOD_ALGO_NO_MULTIMEM);
     if ((flags & SOD_DEBUG_TIMING) && workspace_bytes >= bn_ws_layout(channels, nullptr, nullptr) + kMaxGrid * 32)
         p.w.stamps = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + bn_ws_layout(channels, nullptr, nullptr));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    return SOD_DISPATCH_DTYPE(dtype, T, [&]() -> int { return launch_bn(syncbn_bwd_kernel<T>, &p, p.g, nstream, s); });
+    return SOD_DISPATCH_DTYPE(dtype, T, [&]() -> int {
+        return fold ? launch_bn(syncbn_bwd_kernel<T, 24>, &p, p.g, nstream, s) : launch_bn(syncbn_bwd_kernel<T, 16>, &p, p.g, nstream, s);
+    });
 }

@@ -42,6 +42,29 @@ def bn_act(bn: nn.Module, x: torch.Tensor, *, relu: bool = True,
     return F.relu(y) if relu else y
 
 
+def _conv_nobias(conv: nn.Conv2d, x: torch.Tensor):
+    """(conv(x) WITHOUT its bias, the bias tensor that has to be added later or None)"""
+    if conv.bias is None:
+        return conv(x), None
+    if hasattr(conv, "_sod_w16") and torch.is_autocast_enabled() and x.is_cuda:    # bf16 shadow weights (amp.py)
+        return conv._conv_forward(x, conv._sod_w16, None), conv._sod_b16
+    return conv._conv_forward(x, conv.weight, None), conv.bias
+
+
+def conv_bn_act(conv: nn.Conv2d, bn: nn.Module, x: torch.Tensor, *, relu: bool = True, pre=None,
+                residual: torch.Tensor | None = None) -> torch.Tensor:
+    """y = act( BN( conv(x) [+ pre_conv(pre_x)] ) [+ residual] ) with `pre = (pre_conv, pre_x)`.
+
+    On the B200 engine the convolution biases are not added by a separate elementwise pass (and their gradients not
+    reduced by a separate kernel): the SyncBN kernel folds them in (`conv_bias=`) and its backward produces Σ dz."""
+    fused = getattr(bn, "fused_forward", None)
+    if fused is not None and x.is_cuda:
+        a, b1 = _conv_nobias(conv, x)
+        p, b2 = _conv_nobias(pre[0], pre[1]) if pre is not None else (None, None)
+        return fused(a, pre_add=p, residual=residual, relu=relu, conv_bias=(b1, b2))
+    return bn_act(bn, conv(x), relu=relu, pre_add=None if pre is None else pre[0](pre[1]), residual=residual)
+
+
 # torch.autocast lists upsample_bilinear2d as an fp32 op: under bf16 autocast every interpolate becomes
 # cast-up → fp32 kernel → fp32 result that then drags the following adds into fp32 (≈2 ms of casts per iteration on
 # the TestModel).  The B200 engine sets this flag so the interpolation runs natively in the activation dtype
@@ -209,10 +232,10 @@ class SIM(nn.Module):
         hw = x.shape[2:]
         down = lambda t: avgpool2(self.h2l_pool, t)  # noqa: E731
         # stage 0: split into the two streams
-        xh = bn_act(self.bnh_0, self.h2h_0(x))
-        xl = bn_act(self.bnl_0, self.h2l_0(down(x)))
+        xh = conv_bn_act(self.h2h_0, self.bnh_0, x)
+        xl = conv_bn_act(self.h2l_0, self.bnl_0, down(x))
         # stage 1: cross exchange
-        h_new = bn_act(self.bnh_1, self.h2h_1(xh), pre_add=self.l2h_1(bilinear(xl, size=hw)))
-        l_new = bn_act(self.bnl_1, self.l2l_1(xl), pre_add=self.h2l_1(down(xh)))
+        h_new = conv_bn_act(self.h2h_1, self.bnh_1, xh, pre=(self.l2h_1, bilinear(xl, size=hw)))
+        l_new = conv_bn_act(self.l2l_1, self.bnl_1, xl, pre=(self.h2l_1, down(xh)))
         # stage 2: merge to full-res
-        return bn_act(self.bnh_2, self.h2h_2(h_new), pre_add=self.l2h_2(bilinear(l_new, size=hw)))
+        return conv_bn_act(self.h2h_2, self.bnh_2, h_new, pre=(self.l2h_2, bilinear(l_new, size=hw)))

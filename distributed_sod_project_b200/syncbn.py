@@ -79,7 +79,8 @@ def _as_rows(t: torch.Tensor) -> torch.Tensor:
 
 class _SyncBNFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, pre_add, residual, weight, bias, running_mean, running_var, nbt, momentum, eps, relu, training):
+    def forward(ctx, x, pre_add, residual, weight, bias, running_mean, running_var, nbt, momentum, eps, relu, training,
+                cb1=None, cb2=None):
         x = _as_rows(x)
         pre = _as_rows(pre_add).to(x.dtype) if pre_add is not None else None
         res = _as_rows(residual).to(x.dtype) if residual is not None else None
@@ -91,6 +92,10 @@ class _SyncBNFn(torch.autograd.Function):
         dev = x.device
         mean = torch.empty(c, dtype=torch.float32, device=dev)
         invstd = torch.empty(c, dtype=torch.float32, device=dev)
+        cbs = [t for t in (cb1, cb2) if t is not None]
+        cb_dtype = _lib.dtype_code(cbs[0].dtype) if cbs else 0
+        if len(cbs) == 2 and cbs[0].dtype != cbs[1].dtype:
+            raise _lib.SodError("folded conv biases must share a dtype")
         ws, seq, epoch, cref, soff = _next_call(dev)
         rc = _lib.lib().sod_syncbn_fwd(
             x.data_ptr(), pre.data_ptr() if pre is not None else None, res.data_ptr() if res is not None else None,
@@ -98,12 +103,14 @@ class _SyncBNFn(torch.autograd.Function):
             running_mean.data_ptr() if running_mean is not None else None,
             running_var.data_ptr() if running_var is not None else None,
             mean.data_ptr(), invstd.data_ptr(), rows, c, float(momentum), float(eps), int(relu), int(training),
-            cref, soff, seq, epoch, nbt.data_ptr() if nbt is not None else None, ws.data_ptr(), ws.numel(), DEBUG_FLAGS,
-            _lib.stream_ptr())
+            cref, soff, seq, epoch, nbt.data_ptr() if nbt is not None else None,
+            cb1.data_ptr() if cb1 is not None else None, cb2.data_ptr() if cb2 is not None else None, cb_dtype,
+            ws.data_ptr(), ws.numel(), DEBUG_FLAGS, _lib.stream_ptr())
         _lib.check(rc, "sod_syncbn_fwd")
         _lib.count_launch()
         ctx.relu, ctx.has_pre, ctx.has_res = bool(relu), pre is not None, res is not None
         ctx.weight_ref, ctx.bias_ref = weight, bias
+        ctx.cb = (cb1, cb2)
         ctx.save_for_backward(x, pre, y if relu else None, weight, mean, invstd)
         return y
 
@@ -115,15 +122,27 @@ class _SyncBNFn(torch.autograd.Function):
         wg, bg = getattr(ctx.weight_ref, "grad", None), getattr(ctx.bias_ref, "grad", None)
         direct = (wg is not None and bg is not None and wg.dtype == torch.float32 and bg.dtype == torch.float32
                   and wg.is_contiguous() and bg.is_contiguous() and ctx.weight_ref.requires_grad and ctx.bias_ref.requires_grad)
+        # folded conv biases: the kernel adds Σ_rows dz into a bound .grad (FusedSGD's bf16/fp32 flat buffers) when there
+        # is one, else into a zeroed temporary that is handed to autograd
+        cb1, cb2 = ctx.cb
+        dcb, ret_cb = [None, None], [None, None]
+        for i, cb in enumerate((cb1, cb2)):
+            if cb is None or not cb.requires_grad:
+                continue
+            gbound = getattr(cb, "grad", None)
+            if gbound is not None and gbound.dtype == cb.dtype and gbound.is_contiguous():
+                dcb[i] = gbound
+            else:
+                dcb[i] = torch.zeros_like(cb)
+                ret_cb[i] = dcb[i]
         dz, dres, dgamma, dbeta = raw_backward(_as_rows(dy).to(x.dtype), x, pre, y, weight, mean, invstd, ctx.relu, ctx.has_res,
-                                               into=(wg, bg) if direct else None)
-        if direct:
-            return (dz, dz if ctx.has_pre else None, dres, None, None, None, None, None, None, None, None, None)
-        return (dz, dz if ctx.has_pre else None, dres, dgamma.to(weight.dtype), dbeta.to(weight.dtype),
-                None, None, None, None, None, None, None)
+                                               into=(wg, bg) if direct else None, conv_bias=(cb1, cb2), dconv_bias=dcb)
+        gw, gb = (None, None) if direct else (dgamma.to(weight.dtype), dbeta.to(weight.dtype))
+        return (dz, dz if ctx.has_pre else None, dres, gw, gb, None, None, None, None, None, None, None, ret_cb[0], ret_cb[1])
 
 
-def raw_backward(dy, x, pre, y, weight, mean, invstd, relu: bool, want_dres: bool, into=None):
+def raw_backward(dy, x, pre, y, weight, mean, invstd, relu: bool, want_dres: bool, into=None, conv_bias=(None, None),
+                 dconv_bias=(None, None)):
     """one `sod_syncbn_bwd` launch on channels-last tensors; returns (dz, dres|None, dgamma, dbeta).
     `into=(weight_grad, bias_grad)`: accumulate the parameter gradients into those fp32 tensors instead."""
     n, c, h, w = x.shape
@@ -141,7 +160,10 @@ def raw_backward(dy, x, pre, y, weight, mean, invstd, relu: bool, want_dres: boo
         dy.data_ptr(), x.data_ptr(), pre.data_ptr() if pre is not None else None,
         y.data_ptr() if (relu and y is not None) else None, dz.data_ptr(), dres.data_ptr() if dres is not None else None,
         _lib.dtype_code(x.dtype), weight.data_ptr(), mean.data_ptr(), invstd.data_ptr(), dgamma.data_ptr(),
-        dbeta.data_ptr(), n * h * w, c, int(relu), cref, soff, seq, epoch, ws.data_ptr(), ws.numel(), flags, _lib.stream_ptr())
+        dbeta.data_ptr(), n * h * w, c, int(relu), cref, soff, seq, epoch,
+        *(t.data_ptr() if t is not None else None for t in (conv_bias[0], conv_bias[1], dconv_bias[0], dconv_bias[1])),
+        next((_lib.dtype_code(t.dtype) for t in conv_bias if t is not None), 0),
+        ws.data_ptr(), ws.numel(), flags, _lib.stream_ptr())
     _lib.check(rc, "sod_syncbn_bwd")
     _lib.count_launch()
     return dz, dres, dgamma, dbeta
@@ -153,7 +175,8 @@ class SyncBatchNorm(nn.BatchNorm2d):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return self.fused_forward(x)
 
-    def fused_forward(self, x, pre_add=None, residual=None, relu=False):
+    def fused_forward(self, x, pre_add=None, residual=None, relu=False, conv_bias=(None, None)):
+        """`conv_bias`: biases of the (bias-less) convolutions that produced `x` / `pre_add`, folded into the kernel"""
         if not x.is_cuda:
             raise _lib.SodError("SyncBatchNorm: expected a CUDA tensor (the sm_100a kernel has no CPU fallback; "
                                 "keep nn.BatchNorm2d for CPU runs)")
@@ -170,7 +193,8 @@ class SyncBatchNorm(nn.BatchNorm2d):
         rv = self.running_var if self.track_running_stats else None
         weight = self.weight if self.affine else torch.ones(self.num_features, device=x.device)
         bias = self.bias if self.affine else torch.zeros(self.num_features, device=x.device)
-        return _SyncBNFn.apply(x, pre_add, residual, weight, bias, rm, rv, nbt, momentum, self.eps, relu, training)
+        return _SyncBNFn.apply(x, pre_add, residual, weight, bias, rm, rv, nbt, momentum, self.eps, relu, training,
+                               conv_bias[0], conv_bias[1])
 
 
 def convert_syncbn_model(module: nn.Module, process_group=None, channel_last: bool = True) -> nn.Module:

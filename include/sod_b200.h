@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SOD_ABI_VERSION 3
+#define SOD_ABI_VERSION 4
 #define SOD_MAX_WORLD 8
 #define SOD_MAX_SEGMENTS 16
 #define SOD_COMM_MAX_BLOCKS 1024   /* flag rows per channel */
@@ -140,6 +140,9 @@ int sod_allreduce_f32(const sod_comm* comm, uint64_t off, int64_t n, float scale
  * Data layout: channels-last matrices [M = N*H*W rows, C channels] (dtype ∈ bf16/f16/f32; C a power-of-two
  * multiple of 8, C ≤ 2048), fp32 gamma/beta/running stats/saved stats.
  *   z = x (+ pre_add);  mean/var over M*world rows;  y = relu?((z-mean)*invstd*gamma + beta (+ residual))
+ * conv_bias1/2 (per-channel, dtype conv_bias_dtype, may be NULL): biases of the convolution(s) producing x / pre_add,
+ *   folded in here — z = x (+ pre_add) + b1 + b2 — so that the bias-less convolution output needs no separate
+ *   bias-add pass; the backward adds Σ_rows dz (the bias gradient, LOCAL like dgamma/dbeta) into dconv_bias1/2.
  * training=0: uses running stats, no exchange.  comm may be NULL (world 1).
  * stats_off: arena offset of the exchange slot for this call (sod_syncbn_exchange_bytes(C) bytes; the host
  * rotates ≥2 slots); seq/epoch: the packet tag — it must be unique among all syncbn calls (forward AND
@@ -155,15 +158,17 @@ int sod_syncbn_fwd(const void* x, const void* pre_add, const void* residual, voi
                    const float* gamma, const float* beta, float* running_mean, float* running_var,
                    float* save_mean, float* save_invstd, int64_t rows, int channels, float momentum,
                    float eps, int relu, int training, const sod_comm* comm, uint64_t stats_off, uint32_t seq,
-                   const uint32_t* epoch, int64_t* num_batches_tracked /* += 1 when training; may be NULL */, void* workspace,
+                   const uint32_t* epoch, int64_t* num_batches_tracked /* += 1 when training; may be NULL */,
+                   const void* conv_bias1, const void* conv_bias2, int conv_bias_dtype, void* workspace,
                    size_t workspace_bytes, int flags, void* stream);
 /* dz = d/d(x) = d/d(pre_add); dres = relu-masked dy (written only if non-NULL; may alias nothing);
  * dgamma/dbeta: LOCAL sums (the gradient all-reduce averages them with every other parameter). */
 int sod_syncbn_bwd(const void* dy, const void* x, const void* pre_add, const void* y, void* dz, void* dres,
                    int dtype, const float* gamma, const float* save_mean, const float* save_invstd,
                    float* dgamma, float* dbeta, int64_t rows, int channels, int relu, const sod_comm* comm,
-                   uint64_t stats_off, uint32_t seq, const uint32_t* epoch, void* workspace, size_t workspace_bytes,
-                   int flags, void* stream);
+                   uint64_t stats_off, uint32_t seq, const uint32_t* epoch, const void* conv_bias1,
+                   const void* conv_bias2, void* dconv_bias1, void* dconv_bias2, int conv_bias_dtype, void* workspace,
+                   size_t workspace_bytes, int flags, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Resampling ops on either side of the SyncBN kernels, channels-last [N,H,W,C], C % 8 == 0.

@@ -144,3 +144,41 @@ def test_param_grads_accumulate_into_bound_grad():
     assert torch.allclose(bn2.weight.grad, want_w + 0.5, rtol=1e-5, atol=1e-5)
     assert torch.allclose(bn2.bias.grad, want_b - 0.25, rtol=1e-5, atol=1e-5)
     assert torch.allclose(x2.grad, x.grad)
+
+
+@pytest.mark.parametrize("shape", [(4, 64, 9, 9), (2, 32, 20, 20), (2, 512, 5, 5)])
+@pytest.mark.parametrize("dtype,bdtype", [(torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16)])
+@pytest.mark.parametrize("two", [False, True])
+def test_folded_conv_bias(shape, dtype, bdtype, two):
+    """z = x (+pre) + b1 (+b2) inside the kernel; backward hands back Σ_rows dz as the bias gradient"""
+    n, c, h, w = shape
+    x = _mk(shape, dtype, 31, 1.5, 0.2).requires_grad_(True)
+    pre = _mk(shape, dtype, 32).requires_grad_(True) if two else None
+    g = torch.Generator().manual_seed(33)
+    b1 = torch.randn(c, generator=g).to(bdtype).cuda().requires_grad_(True)
+    b2 = torch.randn(c, generator=g).to(bdtype).cuda().requires_grad_(True) if two else None
+    if two:      # second bias: gradient accumulated into a pre-bound .grad, first one returned through autograd
+        b2.grad = torch.full_like(b2, 0.5)
+    bn = _bn(c)
+    y = bn.fused_forward(x, pre_add=pre, relu=True, conv_bias=(b1, b2))
+    dy = _mk(shape, dtype, 34)
+    y.backward(dy)
+    torch.cuda.synchronize()
+    f64 = lambda t: t.detach().float().cpu().numpy().astype(np.float64)  # noqa: E731
+    btot = f64(b1) + (f64(b2) if two else 0.0)
+    xin = f64(x) + btot[None, :, None, None]
+    ref = obn.syncbn_forward([xin], f64(bn.weight), f64(bn.bias), np.zeros(c), np.ones(c),
+                             pre_adds=[f64(pre)] if two else None, relu=True)
+    tol = _tol(dtype)
+    np.testing.assert_allclose(f64(y), ref["ys"][0], **tol)
+    np.testing.assert_allclose(f64(bn.running_mean), ref["running_mean"], rtol=1e-3, atol=2e-3 if dtype != torch.float32 else 1e-5)
+    rb = obn.syncbn_backward([f64(dy)], ref["zs"], [f64(y)], ref["mean"], ref["invstd"], f64(bn.weight), relu=True)
+    gscale = max(np.abs(rb["dzs"][0]).max(), 1e-6)
+    btol = 3e-2 if dtype != torch.float32 else 3e-4
+    assert np.abs(f64(x.grad) - rb["dzs"][0]).max() / gscale < btol
+    want_db = rb["dzs"][0].sum(axis=(0, 2, 3))          # ≈ 0 at world 1: BN output does not depend on the bias
+    scale = np.abs(rb["dzs"][0]).sum(axis=(0, 2, 3)).max()
+    assert np.abs(f64(b1.grad) - want_db).max() <= (2e-2 if dtype != torch.float32 else 1e-4) * scale + 1e-6
+    if two:
+        assert np.abs(f64(b2.grad) - 0.5 - want_db).max() <= (2e-2 if dtype != torch.float32 else 1e-4) * scale + 8e-3
+        assert torch.equal(pre.grad, x.grad)
