@@ -159,6 +159,28 @@ def _w_syncbn(rank, world):
         np.testing.assert_allclose(f64(bn.weight.grad), rb["dgammas"][rank], rtol=3e-2 if dtype != torch.float32 else 1e-3,
                                    atol=(3e-1 if dtype != torch.float32 else 1e-3))
         torch.distributed.barrier()
+    # folded conv bias across ranks: the bias gradient is the LOCAL Σ dz (non-zero per rank, zero in the rank sum)
+    shape, c = (4, 64, 12, 12), 64
+    g = torch.Generator().manual_seed(77)
+    b_cpu = torch.randn(c, generator=g)
+    xs = [(torch.randn(shape, generator=torch.Generator().manual_seed(500 + r)) * (1 + r) + 0.3 * r) for r in range(world)]
+    dys = [torch.randn(shape, generator=torch.Generator().manual_seed(600 + r)) for r in range(world)]
+    bn = SyncBatchNorm(c).cuda()
+    b = b_cpu.cuda().requires_grad_(True)
+    x = xs[rank].cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    y = bn.fused_forward(x, relu=True, conv_bias=(b, None))
+    y.backward(dys[rank].cuda().contiguous(memory_format=torch.channels_last))
+    torch.cuda.synchronize()
+    f64 = lambda t: t.detach().float().cpu().numpy().astype(np.float64)  # noqa: E731
+    bb = f64(b_cpu)[None, :, None, None]
+    ref = obn.syncbn_forward([f64(t) + bb for t in xs], f64(bn.weight), f64(bn.bias), np.zeros(c), np.ones(c), relu=True)
+    np.testing.assert_allclose(f64(y), ref["ys"][rank], rtol=1e-4, atol=1e-4)
+    ys_mask = [ref["ys"][r] for r in range(world)]; ys_mask[rank] = f64(y)
+    rb = obn.syncbn_backward([f64(t) for t in dys], ref["zs"], ys_mask, ref["mean"], ref["invstd"], f64(bn.weight), relu=True)
+    np.testing.assert_allclose(f64(x.grad), rb["dzs"][rank], rtol=2e-3, atol=2e-4)
+    want_db = rb["dzs"][rank].sum(axis=(0, 2, 3))
+    assert np.abs(want_db).max() > 1e-2                      # genuinely non-zero per rank
+    np.testing.assert_allclose(f64(b.grad), want_db, rtol=2e-3, atol=2e-3)
     from distributed_sod_project_b200 import comm
     comm.small_arena().check_error()
 
