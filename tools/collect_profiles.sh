@@ -13,9 +13,6 @@ timeout 500 ncu --nvtx --nvtx-include "timed" --graph-profiling node --metrics g
     --log-file $O/r01_ncu_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/ncu_launches.out 2>&1
 # 3. full captures of the hand-written kernels (one big SyncBN layer fwd+bwd; loss; fused SGD inside a real iteration, eager)
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:syncbn -c 6 -f -o $O/r01_syncbn_full python tools/bn_one.py > $O/ncu_bn.out 2>&1
-timeout 400 ncu --set full --clock-control none --import-source on -k "regex:loss_bce_cel|sgd_local|upsample2x|avgpool2x2" -s 12 -c 8 -f -o $O/r01_loss_sgd_resample_full \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graph > $O/ncu_loss.out 2>&1
 # 4. per-layer SyncBN table, torch profiler breakdown
 timeout 150 python tools/bn_table.py > $O/r01_syncbn_per_layer.txt 2>/dev/null
-SOD_BENCH_PROFILE=$O/r01_torch_profiler_sod.txt timeout 200 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 ls -la $O | tail -20
