@@ -150,9 +150,13 @@ def test_bf16_shadow_weights_do_not_change_the_trajectory():
             assert float(tr.optimizer.flat.grad16.abs().max()) == 0.0
     assert res[True][0] == pytest.approx(res[False][0], rel=1e-6)       # identical forward
     da, db = res[True][1], res[False][1]
+    import re
     flat = tr.optimizer.flat
+    names = {id(p): n for n, p in tr.module.named_parameters()}
     for p, off in flat.slots:
+        if re.match(r"sim\d+\.(h2|l2)\w+\.bias$", names[id(p)]):
+            continue          # conv bias in front of a BN: mathematically zero gradient, what is left is rounding noise
         a, b = da[off:off + p.numel()], db[off:off + p.numel()]
         scale = float(b.abs().max())
-        if scale > 1e-5:      # conv biases in front of a BN have a mathematically zero gradient: pure noise, skipped
-            assert float((a - b).abs().max()) <= 0.1 * scale
+        if scale > 1e-5:
+            assert float((a - b).abs().max()) <= 0.1 * scale, names[id(p)]
