@@ -364,7 +364,9 @@ def run_b200_arm(args):
     roof = {"bound": "hbm", "kernel": "syncbn_bwd_kernel (84 launches/iteration, replayed alone on the model's layer shapes, "
                                       "L2 flushed between launches)",
             "achieved": bw, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": bw / pk["hbm_gbs"], "peak_kind": pk_kind,
-            "traffic": None, "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": avg_bytes}
+            "traffic": None, "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": avg_bytes,
+            "traffic_note": "per-launch DRAM traffic is only available from ncu for single layers: [16,64,160,160] bf16 backward moves "
+                            "244.8 MB read + 29.7 MB written in-kernel against 209.7 MB algorithmic (profiles/r01_syncbn_full_raw.csv)"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",

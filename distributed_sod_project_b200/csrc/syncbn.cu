@@ -36,7 +36,6 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kBlock = kThreads + 32;     // + one producer warp that only issues bulk copies
 constexpr int kMaxC = 2048;
 constexpr int kMaxStages = 16;
-constexpr int kMaxStreams = 4;
 constexpr int kMaxGrid = 160;
 constexpr int kRedBytes = 49152;          // scratch of the CTA reduction: kWarps x 24 statistics x 32 lanes x 4 B
 constexpr int kSmemFixed = 256 /*barriers*/ + kRedBytes + 3 * kMaxC * 4 /*coefficients*/;

@@ -9,8 +9,8 @@ Written from scratch for this repo; the *contract* it keeps is the reference's
   (so reference checkpoints load, and `make_optimizer("f3_trick")` groups by the same
   `div_2` / `div*` prefixes, `utils/pipeline_ops.py:295-303`);
 * RNG consumption order at construction, so that `init_seed(0)` followed by the factory call
-  yields bit-identical initial weights to the reference (checked by tests/test_network_parity.py
-  when /root/reference is present).
+  yields bit-identical initial weights to the reference (checked by
+  tests/test_host_cpu.py::test_model_plugin_is_bit_identical_to_reference when /root/reference is present).
 
 Every BatchNorm site goes through :func:`bn_act`, which is where the B200 engine hooks in:
 after `convert_syncbn_model` the BN modules expose `fused_forward`, and the (pre-add → BN →

@@ -17,8 +17,6 @@ gradient averaging, so nothing else runs between backward and the next forward.
 """
 from __future__ import annotations
 
-import math
-
 import numpy as np
 import torch
 import torch.nn as nn

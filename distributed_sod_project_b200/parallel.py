@@ -14,12 +14,11 @@ in-place peer-memory all-reduce of the flat gradient buffer at the end of backwa
 """
 from __future__ import annotations
 
-import torch
 import torch.distributed as dist
 import torch.nn as nn
 from torch.autograd import Variable
 
-from . import _lib, comm
+from . import comm
 from .optim import FlatParams, FusedSGD, flat_registry as _flat_registry
 
 

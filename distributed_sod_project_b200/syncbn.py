@@ -14,8 +14,6 @@ Inputs are processed as channels-last [N·H·W, C] matrices; other layouts are c
 """
 from __future__ import annotations
 
-import ctypes as C
-
 import torch
 import torch.nn as nn
 

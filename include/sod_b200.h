@@ -27,7 +27,8 @@ extern "C" {
 #define SOD_MAX_WORLD 8
 #define SOD_MAX_SEGMENTS 16
 #define SOD_COMM_MAX_BLOCKS 1024   /* flag rows per channel */
-#define SOD_COMM_CHANNELS 4        /* 0: grad reduce  1: syncbn fwd  2: syncbn bwd  3: plain all-reduce */
+#define SOD_COMM_CHANNELS 4        /* barrier channels: 0 gradient reduce+SGD, 3 plain all-reduce (1,2 reserved; the
+                                      SyncBN exchange uses tagged packets, not flags) */
 
 typedef enum { SOD_F32 = 0, SOD_BF16 = 1, SOD_F16 = 2 } sod_dtype;
 
@@ -77,7 +78,7 @@ typedef struct {
     uint64_t mc;
     uint64_t arena_bytes;
     uint32_t* error_flag;   /* device word in local memory; set non-zero on a barrier timeout */
-    uint64_t timeout_cycles;/* bounded spin; 0 = default (~20 s) */
+    uint64_t timeout_cycles;/* bounded spin in SM clock cycles; 0 = default (~20 s for barriers, ~2 s for packets) */
     uint32_t* block_seq;    /* device array [SOD_COMM_CHANNELS*SOD_COMM_MAX_BLOCKS] in LOCAL memory, zeroed once:
                                per-block barrier sequence numbers, advanced by the kernels themselves, so the
                                collectives carry no host-side sequence number and replay inside CUDA graphs */

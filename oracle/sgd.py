@@ -16,7 +16,6 @@ result can be compared tightly; `sgd_step_f64` gives the exact-arithmetic answer
 """
 from __future__ import annotations
 
-import math
 from dataclasses import dataclass
 
 import numpy as np

@@ -15,7 +15,7 @@ the stock torch module refuses CPU tensors, torch/nn/modules/batchnorm.py:798-81
 
 `model_factory` is injected: tools/make_golden.py passes the UNMODIFIED reference `network.res50`
 (imported from /root/reference in the build container); the GPU box passes this repo's plugin of the
-same architecture (bit-identical init and outputs, tests/test_network_parity.py).
+same architecture (bit-identical init and outputs: tests/test_host_cpu.py::test_model_plugin_is_bit_identical_to_reference).
 """
 from __future__ import annotations
 
@@ -24,7 +24,6 @@ import time
 import torch
 import torch.distributed as dist
 import torch.nn as nn
-import torch.nn.functional as F
 
 
 # ----------------------------------------------------------------------------------------------

@@ -2,7 +2,6 @@
 (tools/make_golden.py).  CPU only."""
 import numpy as np
 import pytest
-import torch
 
 from oracle import loss as oloss
 from oracle import sgd as osgd
@@ -35,7 +34,6 @@ def _segments(g, kind, it):
     """one Segment per parameter tensor, lr/wd from the reference optimizer's group"""
     names = list(g[f"{kind}/names"])
     group_of = g[f"{kind}/group_of"]
-    import torch.nn as nn
     sizes = {"div_2.weight": 35, "div_2.bias": 7, "div_4.weight": 42, "div_4.bias": 6, "div_16.weight": 18,
              "head.weight": 6, "head.bias": 2, "classifier.weight": 2, "classifier.bias": 1}
     segs, off = [], 0

@@ -5,7 +5,7 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
-from oracle.step import OracleCEL, f3_trick_groups, total_loss
+from oracle.step import OracleCEL, total_loss
 from distributed_sod_project_b200 import network
 from distributed_sod_project_b200.utils import init_seed
 from distributed_sod_project_b200.synthetic import synth_batch

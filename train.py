@@ -23,7 +23,7 @@ import torch
 import torch.distributed as dist
 
 from config import user_config
-from distributed_sod_project_b200 import amp, comm
+from distributed_sod_project_b200 import amp
 from distributed_sod_project_b200.engine import Trainer
 from distributed_sod_project_b200.synthetic import synth_batch
 from distributed_sod_project_b200.utils import (AvgMeter, check_mkdir, construct_exp_name, construct_path_dict, construct_print,
