@@ -4,6 +4,7 @@ Extra keys (all optional, defaults reproduce the B200 benchmark configuration):
   dtype           "bf16" | "fp16" | "fp32": autocast dtype used when `use_amp` is True
   channels_last   run the network in NHWC (what cuDNN's Blackwell kernels and the SyncBN kernels want)
   synthetic       train on synthetic batches of the dataloader's output contract (no dataset on this machine)
+  cuda_graph      capture one iteration per (shape, lr) and replay it: one launch instead of ~700 kernel launches
 """
 import os
 from collections import OrderedDict
@@ -64,6 +65,7 @@ user_config = {
     "channels_last": True,
     "synthetic": True,
     "synthetic_iters_per_epoch": 20,
+    "cuda_graph": True,           # replay each iteration as one CUDA graph (ignored with multi-scale `size_list`)
 }
 
 # test hook: SOD_CONFIG_JSON='{"epoch_num": 1, ...}' overrides keys without editing this file

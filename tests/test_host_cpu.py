@@ -146,3 +146,36 @@ def test_exp_name_and_paths():
     assert name.startswith(config.user_config["model"] + "_SIZE320_BS")
     paths = construct_path_dict(config.user_config["proj_root"], name, config.user_config["xlsx_name"])
     assert paths["final_full_net"].endswith("pth/checkpoint_final.pth.tar")
+
+
+def test_shadow_weight_installation_is_structural_only():
+    """amp's bf16 shadow: every managed Conv2d gets bf16 leaves that alias the flat shadow / gradient buffers; without
+    autocast (eval, CPU) the patched forward still runs on the fp32 master, so outputs are unchanged."""
+    from distributed_sod_project_b200 import amp, network
+    from distributed_sod_project_b200.optim import make_optimizer
+    from distributed_sod_project_b200.utils import init_seed
+    init_seed(0)
+    ref = network.res50().eval()
+    init_seed(0)
+    m = network.res50().eval()
+    opt = make_optimizer(m, "f3_trick", dict(lr=0.05, momentum=0.9, weight_decay=5e-4, nesterov=False))
+    flat = opt.flat
+    flat.enable_shadow(torch.bfloat16)
+    n = amp._install_shadow_weights(m, flat)
+    assert n == sum(isinstance(x, nn.Conv2d) for x in m.modules()) == 105
+    conv = m.sim8.h2h_1
+    lo, hi = flat.shadow16.data_ptr(), flat.shadow16.data_ptr() + 2 * flat.numel
+    assert lo <= conv._sod_w16.data_ptr() < hi and lo <= conv._sod_b16.data_ptr() < hi
+    assert conv._sod_w16.dtype == torch.bfloat16 and conv._sod_w16.requires_grad and conv._sod_w16.grad is not None
+    assert conv._sod_w16.grad.data_ptr() - flat.grad16.data_ptr() == conv._sod_w16.data_ptr() - flat.shadow16.data_ptr()
+    assert torch.equal(conv._sod_w16.detach().float(), conv.weight.detach().to(torch.bfloat16).float())
+    frozen = m.div_2[0]
+    assert frozen._sod_w16.requires_grad                       # div_2 still receives gradients (it is only left un-optimised)
+    x = torch.randn(1, 3, 64, 64)
+    with torch.no_grad():
+        assert torch.equal(m(x), ref(x))
+    # a state_dict load refreshes the shadow
+    sd = ref.state_dict()
+    sd["classifier.weight"] = sd["classifier.weight"] + 1.0
+    m.load_state_dict(sd)
+    assert torch.equal(m.classifier._sod_w16.detach().float(), m.classifier.weight.detach().to(torch.bfloat16).float())
