@@ -91,7 +91,9 @@ def main_worker(local_rank, ngpus_per_node, world_size, args, exp_name, path_con
     trainer = Trainer(model_name=cfg["model"], lr=cfg["lr"], momentum=cfg["momentum"], weight_decay=cfg["weight_decay"],
                       nesterov=cfg["nesterov"], optim=cfg["optim"], reduction=cfg["reduction"], use_aux_loss=cfg["use_aux_loss"],
                       dtype=dtype, channels_last=cfg.get("channels_last", True), report_items=True,
-                      use_graph=cfg.get("cuda_graph", False) and cfg["size_list"] is None)
+                      # a captured iteration bakes its shapes and learning rates: multi-scale batches and a per-iteration
+                      # schedule (`sche_usebatch`) would re-capture every step, so they run eagerly
+                      use_graph=cfg.get("cuda_graph", False) and cfg["size_list"] is None and not cfg["sche_usebatch"])
     scheduler = trainer.scheduler(total_iter_num if cfg["sche_usebatch"] else cfg["epoch_num"], cfg["lr_type"], cfg["lr_decay"],
                                   cfg["warmup_epoch"])
     if local_rank == 0:
