@@ -228,13 +228,22 @@ class TorchEagerTrainer:
     bf16 autocast, channels-last): NOT the reference arm — the "what you get without this repo's kernels" line."""
 
     def __init__(self, model_name, dtype):
-        from oracle.step import OracleCEL, f3_trick_groups
         from distributed_sod_project_b200 import network
         from distributed_sod_project_b200.utils import init_seed
+
+        class StockCEL(torch.nn.Module):          # loss/CEL.py:15-20 in plain torch ops (this arm must not use oracle/)
+            def forward(self, pred, target):
+                p = pred.sigmoid()
+                inter = p * target
+                return ((p - inter).sum() + (target - inter).sum()) / (p.sum() + target.sum() + 1e-6)
+
         init_seed(0)
         self.model = getattr(network, model_name)().cuda().to(memory_format=torch.channels_last)
-        self.opt = torch.optim.SGD(f3_trick_groups(self.model, 0.05), momentum=0.9, weight_decay=5e-4, fused=True)
-        self.loss_funcs = [torch.nn.BCEWithLogitsLoss(), OracleCEL()]
+        named = list(self.model.named_parameters())
+        groups = [{"params": [p for n, p in named if n.startswith("div") and not n.startswith("div_2")], "lr": 0.005},
+                  {"params": [p for n, p in named if not n.startswith("div")], "lr": 0.05}]
+        self.opt = torch.optim.SGD(groups, momentum=0.9, weight_decay=5e-4, fused=True)
+        self.loss_funcs = [torch.nn.BCEWithLogitsLoss(), StockCEL()]
         self.dtype = dtype
         self.world = 1
         self.model.train()
