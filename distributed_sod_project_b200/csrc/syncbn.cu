@@ -10,8 +10,12 @@
 // Layout: channels-last matrix [rows = N·H·W, C].  One persistent CTA per SM owns a contiguous strip
 // of rows (= a contiguous byte range), every thread owns one fixed group of 8 channels.
 //
-//   stage   the strip is pulled through a ring of shared-memory stages by 1-D bulk async copies
-//           (TMA engine, mbarrier completion): ≈180 KB per SM in flight with no registers tied up;
+//   stage   the strip is pulled through a ring of shared-memory stages (32-48 KB each) by 1-D bulk async
+//           copies (TMA engine, mbarrier completion) issued by a dedicated producer warp: ≈150 KB per
+//           SM in flight with no registers tied up (geometry from tools/membench.cu: a bulk-copy ring
+//           delivers ∝ bytes per stage; 32 KB reaches ≈7 TB/s, 8 KB only 3);
+//   fold    biases of the convolutions that produced x / pre_add are added here (z = x + pre + b),
+//           and their gradient Σ dz comes out of the backward's own statistics;
 //   phase 1 per-thread fp32 partial sums straight from shared memory → CTA total [2C];
 //   hop 1   the CTA total is written as 8-byte {value, tag} packets; CTA b then owns a slice of the
 //           2C entries, waits for the packets of all CTAs (spins on the tag — an 8-byte store is
