@@ -360,6 +360,29 @@ def run_b200_arm(args):
     if tr.world > 1 and hasattr(tr.model, "arena") and tr.model.arena is not None:
         tr.model.arena.check_error()
 
+    # -- measurements that ride along (BASELINE metric also names the all-reduce bus bandwidth); every rank takes part,
+    #    nothing in here may prevent the line from being printed -----------------------------------------------------
+    extras = {}
+    try:
+        opt, flat = tr.optimizer, tr.optimizer.flat
+        for _ in range(3):
+            opt.step()                                   # the fused (merge +) all-reduce + SGD kernel(s) alone
+        us_step = timed(lambda i: opt.step(), 10) / 10 * 1e3
+        n_real = sum(p.numel() for p, _ in flat.slots)
+        if world > 1:
+            bus = 2.0 * (world - 1) / world * 4.0 * flat.numel / (us_step * 1e-6) / 1e9
+            extras["fused_allreduce_sgd"] = {"us": us_step, "flat_elems": flat.numel, "params": n_real, "bus_gbs": bus,
+                                             "frac_of_nvlink_900": bus / 900.0,
+                                             "note": "reduce-scatter(grad) + SGD + all-gather(param) in one kernel"
+                                                     + (" (+ bf16 gradient merge pre-pass)" if flat.grad16 is not None else "")}
+        else:
+            per = 30 if flat.grad16 is not None else 24
+            gbs = per * flat.numel / (us_step * 1e-6) / 1e9
+            extras["fused_sgd"] = {"us": us_step, "flat_elems": flat.numel, "bytes_per_elem": per, "gbs": gbs,
+                                   "frac_of_hbm": gbs / peaks()[0]["hbm_gbs"]}
+    except Exception as ex:                              # noqa: BLE001
+        extras["step_error"] = repr(ex)
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -387,6 +410,29 @@ def run_b200_arm(args):
             "clocks": clk.summary(),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "roofline": roof}
+    try:        # the loss kernel alone: at the workload shape (latency bound) and at SURVEY §8d's scaled shape
+        from distributed_sod_project_b200.loss import bce_cel_fwd_bwd
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        for tag, shape in (("loss_workload", (BS, 1, SIZE, SIZE)), ("loss_scaled", (64, 1, 1024, 1024))):
+            lx = torch.randn(shape, device="cuda").to(dtype)
+            lt = (torch.rand(shape, device="cuda") > 0.8).float()
+            ts = []
+            for _ in range(7):
+                flush.zero_()
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                bce_cel_fwd_bwd(lx, lt)
+                e.record()
+                e.synchronize()
+                ts.append(s.elapsed_time(e) * 1e3)
+            us = sorted(ts)[len(ts) // 2]
+            byts = lx.numel() * (2 * lx.element_size() + 4)      # logits in + grad out + fp32 mask in
+            extras[tag] = {"shape": list(shape), "us": us, "algorithmic_bytes": byts, "gbs": byts / (us * 1e-6) / 1e9,
+                           "frac_of_hbm": byts / (us * 1e-6) / 1e9 / pk["hbm_gbs"]}
+            del lx, lt
+    except Exception as ex:                              # noqa: BLE001
+        extras["loss_error"] = repr(ex)
+    line["extras"] = extras
     if not args.no_cpu_baseline:
         res = cpu_reference(args.model, args.cpu_batch, 6, 1)
         line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
