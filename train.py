@@ -24,6 +24,7 @@ import torch.distributed as dist
 
 from config import user_config
 from distributed_sod_project_b200 import amp
+from distributed_sod_project_b200.checkpoint import resume_checkpoint, save_checkpoint
 from distributed_sod_project_b200.engine import Trainer
 from distributed_sod_project_b200.synthetic import synth_batch
 from distributed_sod_project_b200.utils import (AvgMeter, check_mkdir, construct_exp_name, construct_path_dict, construct_print,
@@ -100,7 +101,15 @@ def main_worker(local_rank, ngpus_per_node, world_size, args, exp_name, path_con
         construct_print(f"optimizer = {trainer.optimizer}")
         construct_print(f"scheduler = {scheduler}")
 
-    for curr_epoch in range(cfg["epoch_num"]):
+    start_epoch = 0
+    if cfg["resume_mode"] == "train":
+        # reference train.py:188-198 resumes on rank 0 only (the other ranks keep their initial weights and the
+        # first all-reduce mixes them); here every rank loads the same file
+        start_epoch = resume_checkpoint(model=trainer.model, optimizer=trainer.optimizer, amp=amp if cfg["use_amp"] else None,
+                                        exp_name=exp_name, load_path=path_config["final_full_net"], mode="all",
+                                        local_rank=local_rank)
+
+    for curr_epoch in range(start_epoch, cfg["epoch_num"]):
         loader.set_epoch(curr_epoch)
         if not cfg["sche_usebatch"]:
             scheduler.step(optimizer=trainer.optimizer, curr_epoch=curr_epoch)
@@ -128,11 +137,9 @@ def main_worker(local_rank, ngpus_per_node, world_size, args, exp_name, path_con
             n_img = len(loader) * batch_size_single_gpu * max(world_size, 1)
             construct_print(f"epoch {curr_epoch}: {time.time() - t0:.2f}s, {n_img / (time.time() - t0):.1f} img/s")
             if (cfg["save_freq"] > 0 and (curr_epoch + 1) % cfg["save_freq"] == 0) or curr_epoch == cfg["epoch_num"] - 1:
-                net_state = trainer.module.state_dict()                                 # utils/pipeline_ops.py:68-78 layout
-                torch.save({"arch": exp_name, "epoch": curr_epoch + 1, "net_state": net_state,
-                            "opti_state": trainer.optimizer.state_dict(),
-                            "amp_state": amp.state_dict() if cfg["use_amp"] else None}, path_config["final_full_net"])
-                torch.save(net_state, path_config["final_state_net"])
+                save_checkpoint(model=trainer.model, optimizer=trainer.optimizer, amp=amp if cfg["use_amp"] else None,
+                                exp_name=exp_name, current_epoch=curr_epoch + 1, full_net_path=path_config["final_full_net"],
+                                state_net_path=path_config["final_state_net"])          # utils/pipeline_ops.py:46-78 layout
     construct_print("End Training...")
     if dist.is_initialized():
         arena = getattr(trainer.model, "arena", None)
