@@ -179,3 +179,43 @@ def test_shadow_weight_installation_is_structural_only():
     sd["classifier.weight"] = sd["classifier.weight"] + 1.0
     m.load_state_dict(sd)
     assert torch.equal(m.classifier._sod_w16.detach().float(), m.classifier.weight.detach().to(torch.bfloat16).float())
+
+
+def test_ctypes_prototypes_match_header_argument_by_argument():
+    """every prototype of include/sod_b200.h, parsed from the header text, against the ctypes binding: same number of
+    arguments, same width/kind for each (a mismatch here is a silent stack/registers mix-up on the GPU box)"""
+    import ctypes as C
+    from distributed_sod_project_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "sod_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", " ", text)
+    protos = re.findall(r"\b(int|size_t|const char\s*\*)\s+(sod_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text)
+    assert {name for _, name, _ in protos} == set(_lib.EXPORTS)
+
+    def kind(ctype: str):
+        t = ctype.strip()
+        t = re.sub(r"\s+[A-Za-z_][A-Za-z0-9_]*(\[[0-9A-Z_]*\])?$", "", t) if not t.endswith("*") else t    # drop the name
+        t = re.sub(r"\bconst\b", "", t).replace(" ", "")
+        if t.endswith("*"):
+            base = t[:-1]
+            if base == "sod_comm":
+                return C.POINTER(_lib.sod_comm)
+            if base == "sod_sgd_segment":
+                return C.POINTER(_lib.sod_sgd_segment)
+            return "ptr"
+        return {"int": C.c_int, "int64_t": C.c_int64, "uint64_t": C.c_uint64, "uint32_t": C.c_uint32, "float": C.c_float,
+                "size_t": C.c_size_t, "int32_t": C.c_int32}[t]
+
+    ret = {"int": C.c_int, "size_t": C.c_size_t}
+    for r, name, args in protos:
+        res, bound = _lib._PROTOTYPES[name]
+        assert res == ret.get(r, C.c_char_p), name
+        params = [] if args.strip() in ("", "void") else [a for a in args.split(",")]
+        # "type* name" → split the name off pointers too
+        kinds = [kind(re.sub(r"\*\s*[A-Za-z_][A-Za-z0-9_]*\s*$", "*", p.strip())) for p in params]
+        assert len(kinds) == len(bound), f"{name}: header has {len(kinds)} parameters, binding {len(bound)}"
+        for i, (k, b) in enumerate(zip(kinds, bound)):
+            if k == "ptr":
+                assert b is C.c_void_p or (isinstance(b, type) and issubclass(b, C._Pointer)), f"{name} arg {i}: {b} for a pointer"
+            else:
+                assert k is b or k == b, f"{name} arg {i}: header {k}, binding {b}"
