@@ -19,6 +19,7 @@ SOD_SGD_ZERO_GRAD = 1
 SOD_ALGO_NO_MULTIMEM = 2
 SOD_BN_ACCUMULATE_PARAM_GRADS = 8
 SOD_ALGO_FORCE_MULTIMEM = 16
+SOD_BN_BWD_MASK_FROM_X = 32     # experimental, see include/sod_b200.h
 
 
 class SodError(RuntimeError):
@@ -60,7 +61,7 @@ _PROTOTYPES = {
                                  C.c_int, C.c_int, C.POINTER(sod_comm), C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "sod_syncbn_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
-                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
                                  C.POINTER(sod_comm), C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "sod_upsample2x_bilinear_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),

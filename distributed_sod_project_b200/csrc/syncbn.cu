@@ -103,6 +103,7 @@ struct BnBwd {
     uint32_t tag;
     const uint32_t* epoch;
     int use_mc;
+    const float* beta;            // XMASK only: the ReLU mask is recomputed from x (y is not read)
 };
 
 // folded conv bias of the 8 channels a thread owns (fp32 master or bf16 shadow leaves)
@@ -616,7 +617,11 @@ __global__ void __launch_bounds__(kBlock, 1) syncbn_fwd_kernel(const __grid_cons
 // =================================================================================================
 // backward
 // =================================================================================================
-template <typename T, int NSTAT>
+// XMASK (experimental, SOD_BN_BWD_MASK_FROM_X): a BN+ReLU layer without residual does not stream y at all — the
+// mask y > 0 is re-derived from x with the forward's own arithmetic (y = fma(z, invstd*γ, fma(b, invstd*γ, β - mean*invstd*γ)),
+// same operations in the same order, so the sign agrees with the stored y except where |y| is denormal).  One stream
+// less to read twice: compulsory bytes drop from 4 to 3 tensors, and a third more of the strip stays resident.
+template <typename T, int NSTAT, bool XMASK = false>
 __global__ void __launch_bounds__(kBlock, 1) syncbn_bwd_kernel(const __grid_constant__ BnBwd prm) {
     extern __shared__ __align__(128) unsigned char smem[];
     float* red = reinterpret_cast<float*>(smem + 256);
@@ -643,7 +648,7 @@ __global__ void __launch_bounds__(kBlock, 1) syncbn_bwd_kernel(const __grid_cons
     const int k_pre = 2, k_y = has_pre ? 3 : 2;
     const void* src[4] = {prm.dy, prm.x, nullptr, nullptr};
     if (has_pre) src[k_pre] = prm.pre;
-    if (relu) src[k_y] = prm.y;
+    if (relu && !XMASK) src[k_y] = prm.y;
     const void* const csrc[4] = {src[0], src[1], src[2], src[3]};
     if (tid >= kThreads) {  // ---- producer warp --------------------------------------------------------------
         producer_loop<4>(ring, g, csrc, sp, total_loads, nres0);
@@ -671,6 +676,18 @@ __global__ void __launch_bounds__(kBlock, 1) syncbn_bwd_kernel(const __grid_cons
         cb[k] = kFold ? ld_bias(prm.cbias1, prm.cbias_dtype, l * 8 + k) + ld_bias(prm.cbias2, prm.cbias_dtype, l * 8 + k) : 0.f;
         mean[k] -= cb[k];
     }
+    // XMASK: the forward's scale and shift of this thread's 8 channels (csrc: syncbn_fwd_kernel, "sc" / "sh")
+    float msc[XMASK ? 8 : 1], msh[XMASK ? 8 : 1];
+    if (XMASK) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int ch = l * 8 + k;
+            const float sc = s_b[ch] * s_a[ch];                       // invstd * γ
+            const float sh0 = fmaf(-s_d[ch], sc, prm.beta[ch]);       // β - mean * sc, as the forward contracts it
+            msc[XMASK ? k : 0] = sc;
+            msh[XMASK ? k : 0] = fmaf(cb[k], sc, sh0);
+        }
+    }
 
     // one packet of work, shared by both phases (measured: interleaving two packets per thread only added register
     // pressure here — four streams per packet already give the scheduler independent loads)
@@ -683,7 +700,10 @@ __global__ void __launch_bounds__(kBlock, 1) syncbn_bwd_kernel(const __grid_cons
 #pragma unroll
             for (int k = 0; k < 8; ++k) z[k] += t[k];
         }
-        if (relu) {
+        if (XMASK) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) d[k] = fmaf(z[k], msc[XMASK ? k : 0], msh[XMASK ? k : 0]) > 0.f ? d[k] : 0.f;
+        } else if (relu) {
             float o[8];
             IO<T>::load8(reinterpret_cast<const T*>(ring.buf(s, k_y)) + q * 8, o);
 #pragma unroll
@@ -930,14 +950,18 @@ extern "C" int sod_syncbn_fwd(const void* x, const void* pre_add, const void* re
 }
 
 extern "C" int sod_syncbn_bwd(const void* dy, const void* x, const void* pre_add, const void* y, void* dz, void* dres,
-                              int dtype, const float* gamma, const float* save_mean, const float* save_invstd,
-                              float* dgamma, float* dbeta, int64_t rows, int channels, int relu, const sod_comm* comm,
+                              int dtype, const float* gamma, const float* beta, const float* save_mean,
+                              const float* save_invstd, float* dgamma, float* dbeta, int64_t rows, int channels, int relu,
+                              const sod_comm* comm,
                               uint64_t stats_off, uint32_t seq, const uint32_t* epoch, const void* conv_bias1,
                               const void* conv_bias2, void* dconv_bias1, void* dconv_bias2, int conv_bias_dtype,
                               void* workspace, size_t workspace_bytes, int flags, void* stream) {
     using namespace sod;
     SOD_CHECK_ARG(dy && x && dz && gamma && save_mean && save_invstd && dgamma && dbeta && workspace, SOD_EINVAL);
-    SOD_CHECK_ARG(!relu || y, SOD_EINVAL);
+    // experimental: ReLU mask from x instead of y — only for BN+ReLU without a residual operand
+    const bool xmask = (flags & SOD_BN_BWD_MASK_FROM_X) != 0;
+    SOD_CHECK_ARG(!xmask || (relu && !dres && beta), SOD_EINVAL);
+    SOD_CHECK_ARG(!relu || y || xmask, SOD_EINVAL);
     SOD_CHECK_ARG(aligned16(dy) && aligned16(x) && aligned16(dz) && aligned16(workspace) &&
                       (!pre_add || aligned16(pre_add)) && (!y || aligned16(y)) && (!dres || aligned16(dres)), SOD_EALIGN);
     if (dev_info().cc_major != 10) return SOD_EUNSUPPORTED;
@@ -949,11 +973,12 @@ extern "C" int sod_syncbn_bwd(const void* dy, const void* x, const void* pre_add
         SOD_CHECK_ARG(stats_off >= sod_comm_flag_bytes() &&
                           stats_off + sod_syncbn_exchange_bytes(channels) <= comm->arena_bytes, SOD_ECOMM);
     }
-    const int nstream = 2 + (pre_add ? 1 : 0) + (relu ? 1 : 0);
+    const int nstream = 2 + (pre_add ? 1 : 0) + ((relu && !xmask) ? 1 : 0);
     rc = make_geom(rows, channels, dtype, nstream, p.g);
     if (rc != SOD_OK) return rc;
     if (bn_ws_layout(channels, &p.w, workspace) > workspace_bytes) return SOD_EWORKSPACE;
-    p.dy = dy; p.x = x; p.pre = pre_add; p.y = relu ? y : nullptr; p.dz = dz; p.dres = dres;
+    p.dy = dy; p.x = x; p.pre = pre_add; p.y = (relu && !xmask) ? y : nullptr; p.dz = dz; p.dres = dres;
+    p.beta = beta;
     p.gamma = gamma; p.smean = save_mean; p.sinvstd = save_invstd; p.dgamma = dgamma; p.dbeta = dbeta;
     p.relu = relu; p.stats_off = stats_off; p.tag = seq; p.epoch = epoch;
     p.accumulate = (flags & SOD_BN_ACCUMULATE_PARAM_GRADS) ? 1 : 0;
@@ -964,6 +989,9 @@ extern "C" int sod_syncbn_bwd(const void* dy, const void* x, const void* pre_add
         p.w.stamps = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + bn_ws_layout(channels, nullptr, nullptr));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     return SOD_DISPATCH_DTYPE(dtype, T, [&]() -> int {
+        if (xmask)
+            return fold ? launch_bn(syncbn_bwd_kernel<T, 24, true>, &p, p.g, nstream, s)
+                        : launch_bn(syncbn_bwd_kernel<T, 16, true>, &p, p.g, nstream, s);
         return fold ? launch_bn(syncbn_bwd_kernel<T, 24>, &p, p.g, nstream, s) : launch_bn(syncbn_bwd_kernel<T, 16>, &p, p.g, nstream, s);
     });
 }

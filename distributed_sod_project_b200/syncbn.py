@@ -14,6 +14,8 @@ Inputs are processed as channels-last [N·H·W, C] matrices; other layouts are c
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -22,6 +24,9 @@ from . import _lib, comm
 _state: dict = {}
 DEBUG_FLAGS = 0             # tools/bn_phases.py sets SOD_DEBUG_TIMING (4)
 FORCE_LOCAL = False         # bench.py roofline replay: run single-rank (no exchange) even inside a process group
+# EXPERIMENTAL (written without access to a GPU; off until measured and parity-checked on hardware, then it becomes
+# the default): BN+ReLU layers without a residual re-derive the ReLU mask from x in the backward instead of reading y
+MASK_FROM_X = os.environ.get("SOD_BN_MASK_FROM_X", "0") == "1"
 TRACE: list | None = None   # bench.py: when a list, every forward call appends (n, c, h, w, has_pre, has_res, relu)
 
 
@@ -134,15 +139,17 @@ class _SyncBNFn(torch.autograd.Function):
                 dcb[i] = torch.zeros_like(cb)
                 ret_cb[i] = dcb[i]
         dz, dres, dgamma, dbeta = raw_backward(_as_rows(dy).to(x.dtype), x, pre, y, weight, mean, invstd, ctx.relu, ctx.has_res,
-                                               into=(wg, bg) if direct else None, conv_bias=(cb1, cb2), dconv_bias=dcb)
+                                               into=(wg, bg) if direct else None, conv_bias=(cb1, cb2), dconv_bias=dcb,
+                                               bias=ctx.bias_ref)
         gw, gb = (None, None) if direct else (dgamma.to(weight.dtype), dbeta.to(weight.dtype))
         return (dz, dz if ctx.has_pre else None, dres, gw, gb, None, None, None, None, None, None, None, ret_cb[0], ret_cb[1])
 
 
 def raw_backward(dy, x, pre, y, weight, mean, invstd, relu: bool, want_dres: bool, into=None, conv_bias=(None, None),
-                 dconv_bias=(None, None)):
+                 dconv_bias=(None, None), bias=None):
     """one `sod_syncbn_bwd` launch on channels-last tensors; returns (dz, dres|None, dgamma, dbeta).
-    `into=(weight_grad, bias_grad)`: accumulate the parameter gradients into those fp32 tensors instead."""
+    `into=(weight_grad, bias_grad)`: accumulate the parameter gradients into those fp32 tensors instead.
+    `bias` (β) is only read by the experimental MASK_FROM_X variant."""
     n, c, h, w = x.shape
     dz = torch.empty_like(x)
     dres = torch.empty_like(x) if want_dres else None
@@ -153,11 +160,14 @@ def raw_backward(dy, x, pre, y, weight, mean, invstd, relu: bool, want_dres: boo
         dgamma = torch.empty(c, dtype=torch.float32, device=x.device)
         dbeta = torch.empty(c, dtype=torch.float32, device=x.device)
         flags = DEBUG_FLAGS
+    if MASK_FROM_X and relu and not want_dres and bias is not None:
+        flags |= _lib.SOD_BN_BWD_MASK_FROM_X
     ws, seq, epoch, cref, soff = _next_call(x.device)
     rc = _lib.lib().sod_syncbn_bwd(
         dy.data_ptr(), x.data_ptr(), pre.data_ptr() if pre is not None else None,
         y.data_ptr() if (relu and y is not None) else None, dz.data_ptr(), dres.data_ptr() if dres is not None else None,
-        _lib.dtype_code(x.dtype), weight.data_ptr(), mean.data_ptr(), invstd.data_ptr(), dgamma.data_ptr(),
+        _lib.dtype_code(x.dtype), weight.data_ptr(), bias.data_ptr() if bias is not None else None,
+        mean.data_ptr(), invstd.data_ptr(), dgamma.data_ptr(),
         dbeta.data_ptr(), n * h * w, c, int(relu), cref, soff, seq, epoch,
         *(t.data_ptr() if t is not None else None for t in (conv_bias[0], conv_bias[1], dconv_bias[0], dconv_bias[1])),
         next((_lib.dtype_code(t.dtype) for t in conv_bias if t is not None), 0),

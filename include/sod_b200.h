@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SOD_ABI_VERSION 4
+#define SOD_ABI_VERSION 5
 #define SOD_MAX_WORLD 8
 #define SOD_MAX_SEGMENTS 16
 #define SOD_COMM_MAX_BLOCKS 1024   /* flag rows per channel */
@@ -116,7 +116,10 @@ typedef struct {
 enum { SOD_SGD_ZERO_GRAD = 1, SOD_ALGO_NO_MULTIMEM = 2,
        SOD_DEBUG_TIMING = 4 /* syncbn: per-CTA globaltimer stamps behind the workspace (tools/bn_phases.py) */,
        SOD_BN_ACCUMULATE_PARAM_GRADS = 8 /* syncbn_bwd: dgamma/dbeta += (write straight into the bound .grad) */,
-       SOD_ALGO_FORCE_MULTIMEM = 16 /* use NVLS even at world 2, where the default is peer loads */ };
+       SOD_ALGO_FORCE_MULTIMEM = 16 /* use NVLS even at world 2, where the default is peer loads */,
+       SOD_BN_BWD_MASK_FROM_X = 32 /* syncbn_bwd, EXPERIMENTAL (off by default in the host layer until it has been
+                                      measured on hardware): re-derive the ReLU mask from x with the forward's
+                                      arithmetic instead of reading y; needs relu, beta and dres == NULL */ };
 
 int sod_sgd_momentum(float* param, float* mom, float* grad, void* grad16, void* shadow16, int64_t n,
                      const sod_sgd_segment* segs, int nseg, float inv_scale, const uint32_t* found_inf, int flags,
@@ -163,11 +166,13 @@ int sod_syncbn_fwd(const void* x, const void* pre_add, const void* residual, voi
                    const void* conv_bias1, const void* conv_bias2, int conv_bias_dtype, void* workspace,
                    size_t workspace_bytes, int flags, void* stream);
 /* dz = d/d(x) = d/d(pre_add); dres = relu-masked dy (written only if non-NULL; may alias nothing);
- * dgamma/dbeta: LOCAL sums (the gradient all-reduce averages them with every other parameter). */
+ * dgamma/dbeta: LOCAL sums (the gradient all-reduce averages them with every other parameter).
+ * y: the forward's output, read for the ReLU mask (may be NULL when relu == 0 or with SOD_BN_BWD_MASK_FROM_X);
+ * beta: read only with SOD_BN_BWD_MASK_FROM_X (may be NULL otherwise). */
 int sod_syncbn_bwd(const void* dy, const void* x, const void* pre_add, const void* y, void* dz, void* dres,
-                   int dtype, const float* gamma, const float* save_mean, const float* save_invstd,
-                   float* dgamma, float* dbeta, int64_t rows, int channels, int relu, const sod_comm* comm,
-                   uint64_t stats_off, uint32_t seq, const uint32_t* epoch, const void* conv_bias1,
+                   int dtype, const float* gamma, const float* beta, const float* save_mean,
+                   const float* save_invstd, float* dgamma, float* dbeta, int64_t rows, int channels, int relu,
+                   const sod_comm* comm, uint64_t stats_off, uint32_t seq, const uint32_t* epoch, const void* conv_bias1,
                    const void* conv_bias2, void* dconv_bias1, void* dconv_bias2, int conv_bias_dtype, void* workspace,
                    size_t workspace_bytes, int flags, void* stream);
 

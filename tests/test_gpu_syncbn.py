@@ -1,5 +1,7 @@
 """Parity of the SyncBN kernels (world 1 here; world 2 in test_gpu_multi.py) with the fp64 oracle and with
 torch's own batch_norm autograd."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -182,3 +184,41 @@ def test_folded_conv_bias(shape, dtype, bdtype, two):
     if two:
         assert np.abs(f64(b2.grad) - 0.5 - want_db).max() <= (2e-2 if dtype != torch.float32 else 1e-4) * scale + 8e-3
         assert torch.equal(pre.grad, x.grad)
+
+
+@pytest.mark.skipif(os.environ.get("SOD_EXPERIMENTAL") != "1",
+                    reason="experimental kernel variant (not yet validated on hardware): run with SOD_EXPERIMENTAL=1")
+@pytest.mark.parametrize("shape", [(16, 64, 80, 80), (4, 64, 33, 31), (16, 256, 20, 20), (2, 2048, 2, 2), (16, 32, 160, 160)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("with_pre,with_cb", [(False, False), (True, False), (False, True)])
+def test_bwd_mask_from_x_agrees_with_mask_from_y(shape, dtype, with_pre, with_cb):
+    """SOD_BN_BWD_MASK_FROM_X re-derives the ReLU mask from x: against the default variant on the same inputs the result
+    may differ only by the summation order of the statistics (different strip geometry)."""
+    from distributed_sod_project_b200 import syncbn
+    n, c, h, w = shape
+    x = _mk(shape, dtype, 1, 1.5, 0.3).requires_grad_(True)
+    pre = _mk(shape, dtype, 2) if with_pre else None
+    cb = (torch.linspace(-0.5, 0.5, c, device="cuda").to(dtype).requires_grad_(True), None) if with_cb else (None, None)
+    bn = _bn(c)
+    y = bn.fused_forward(x, pre_add=pre, relu=True, conv_bias=cb)
+    _, _, _, _, mean, invstd = y.grad_fn.saved_tensors
+    dy = _mk(shape, dtype, 4)
+    out = {}
+    for flag in (False, True):
+        syncbn.MASK_FROM_X = flag
+        try:
+            dcb = (torch.zeros_like(cb[0]), None) if with_cb else (None, None)
+            dz, _, dg, db = syncbn.raw_backward(dy, x.detach(), pre, y.detach(), bn.weight.detach(), mean, invstd, True, False,
+                                                conv_bias=tuple(None if t is None else t.detach() for t in cb),
+                                                dconv_bias=dcb, bias=bn.bias.detach())
+        finally:
+            syncbn.MASK_FROM_X = False
+        torch.cuda.synchronize()
+        out[flag] = (dz.float(), dg, db, None if dcb[0] is None else dcb[0].float())
+    scale = float(out[False][0].abs().max())
+    tol = 2e-5 if dtype == torch.float32 else 1e-2
+    assert float((out[False][0] - out[True][0]).abs().max()) <= tol * scale
+    rows = n * h * w
+    for a, b in zip(out[False][1:], out[True][1:]):
+        if a is not None:
+            torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-4 * rows ** 0.5 if dtype == torch.float32 else 2e-2 * rows ** 0.5)
