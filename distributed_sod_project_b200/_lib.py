@@ -20,6 +20,7 @@ SOD_ALGO_NO_MULTIMEM = 2
 SOD_BN_ACCUMULATE_PARAM_GRADS = 8
 SOD_ALGO_FORCE_MULTIMEM = 16
 SOD_BN_BWD_MASK_FROM_X = 32     # experimental, see include/sod_b200.h
+SOD_BN_L2_HINTS = 64            # experimental, see include/sod_b200.h
 
 
 class SodError(RuntimeError):

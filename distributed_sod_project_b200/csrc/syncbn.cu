@@ -237,8 +237,9 @@ __device__ __forceinline__ int chunk_rows_of(const BnGeom& g, long long chunk) {
 }
 
 // thread 0: start the bulk copies of `chunk` (all streams) into stage s
-template <int NS>
-__device__ __forceinline__ void issue_chunk(Ring& ring, const BnGeom& g, const void* const (&src)[NS], int s, long long chunk) {
+template <int NS, bool HINT = false>
+__device__ __forceinline__ void issue_chunk(Ring& ring, const BnGeom& g, const void* const (&src)[NS], int s, long long chunk,
+                                            uint64_t policy = 0) {
     const uint32_t bytes = static_cast<uint32_t>(chunk_rows_of(g, chunk)) * g.C * g.es;
     const size_t off = static_cast<size_t>(chunk) * g.chunk_rows * g.C * g.es;
     int active = 0;
@@ -247,7 +248,10 @@ __device__ __forceinline__ void issue_chunk(Ring& ring, const BnGeom& g, const v
     mbar_arrive_expect_tx(&ring.full[s], bytes * active);
 #pragma unroll
     for (int k = 0; k < NS; ++k)
-        if (src[k] != nullptr) bulk_g2s(ring.buf(s, k), static_cast<const char*>(src[k]) + off, bytes, &ring.full[s]);
+        if (src[k] != nullptr) {
+            if (HINT) bulk_g2s_hint(ring.buf(s, k), static_cast<const char*>(src[k]) + off, bytes, &ring.full[s], policy);
+            else bulk_g2s(ring.buf(s, k), static_cast<const char*>(src[k]) + off, bytes, &ring.full[s]);
+        }
 }
 
 // ---- CTA-level reduction of NA (16 or 24) per-thread accumulators over the threads that share a lane ----------
@@ -385,7 +389,10 @@ __device__ __forceinline__ void ring_setup(Ring& ring, unsigned char* smem, cons
 __device__ __forceinline__ int load_chunk_of(int k, int n, int nres0) { return k < n ? k : nres0 - 1 - (k - n); }
 
 // producer warp: lane 0 keeps the ring full
-template <int NSRC>
+// HINT (experimental, SOD_BN_L2_HINTS): a chunk that phase 2 will have to fetch again (it does not stay resident in
+// shared memory) is loaded evict-last; every last use — the chunks that stay resident, and all phase-2 re-reads — is
+// loaded evict-first, so that the re-read set rather than dead data occupies L2.
+template <int NSRC, bool HINT = false>
 __device__ __forceinline__ void producer_loop(Ring& ring, const BnGeom& g, const void* const (&src)[NSRC], const StripInfo& sp,
                                               int total_loads, int nres0) {
     if ((threadIdx.x & 31) != 0) return;
@@ -393,7 +400,12 @@ __device__ __forceinline__ void producer_loop(Ring& ring, const BnGeom& g, const
     for (int k = 0; k < total_loads; ++k) {
         const int s = k % NS;
         if (k >= NS) ring.wait_empty(s);
-        issue_chunk<NSRC>(ring, g, src, s, sp.chunk0 + load_chunk_of(k, sp.n, nres0));
+        if (HINT) {
+            const bool again = k < sp.n && k < nres0;     // phase-1 load of a chunk that will not stay resident
+            issue_chunk<NSRC, true>(ring, g, src, s, sp.chunk0 + load_chunk_of(k, sp.n, nres0), again ? kL2EvictLast : kL2EvictFirst);
+        } else {
+            issue_chunk<NSRC>(ring, g, src, s, sp.chunk0 + load_chunk_of(k, sp.n, nres0));
+        }
     }
 }
 
@@ -621,7 +633,7 @@ __global__ void __launch_bounds__(kBlock, 1) syncbn_fwd_kernel(const __grid_cons
 // mask y > 0 is re-derived from x with the forward's own arithmetic (y = fma(z, invstd*γ, fma(b, invstd*γ, β - mean*invstd*γ)),
 // same operations in the same order, so the sign agrees with the stored y except where |y| is denormal).  One stream
 // less to read twice: compulsory bytes drop from 4 to 3 tensors, and a third more of the strip stays resident.
-template <typename T, int NSTAT, bool XMASK = false>
+template <typename T, int NSTAT, bool XMASK = false, bool HINT = false>
 __global__ void __launch_bounds__(kBlock, 1) syncbn_bwd_kernel(const __grid_constant__ BnBwd prm) {
     extern __shared__ __align__(128) unsigned char smem[];
     float* red = reinterpret_cast<float*>(smem + 256);
@@ -651,7 +663,7 @@ __global__ void __launch_bounds__(kBlock, 1) syncbn_bwd_kernel(const __grid_cons
     if (relu && !XMASK) src[k_y] = prm.y;
     const void* const csrc[4] = {src[0], src[1], src[2], src[3]};
     if (tid >= kThreads) {  // ---- producer warp --------------------------------------------------------------
-        producer_loop<4>(ring, g, csrc, sp, total_loads, nres0);
+        producer_loop<4, HINT>(ring, g, csrc, sp, total_loads, nres0);
         return;
     }
 
@@ -873,7 +885,7 @@ static size_t bn_ws_layout(int C, BnWork* w, void* base) {
 template <typename K>
 static int launch_bn(K kern, const void* prm, const BnGeom& g, int nstream, cudaStream_t stream) {
     const size_t smem = kSmemFixed + static_cast<size_t>(g.nstage) * nstream * g.chunk_bytes;
-    static thread_local const void* configured[32] = {nullptr};   // per kernel instantiation, once per thread
+    static thread_local const void* configured[64] = {nullptr};   // per kernel instantiation, once per thread
     cudaError_t e;
     bool done = false;
     for (const void* c : configured) done |= (c == reinterpret_cast<const void*>(kern));
@@ -989,6 +1001,13 @@ extern "C" int sod_syncbn_bwd(const void* dy, const void* x, const void* pre_add
         p.w.stamps = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + bn_ws_layout(channels, nullptr, nullptr));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     return SOD_DISPATCH_DTYPE(dtype, T, [&]() -> int {
+        if (flags & SOD_BN_L2_HINTS) {
+            if (xmask)
+                return fold ? launch_bn(syncbn_bwd_kernel<T, 24, true, true>, &p, p.g, nstream, s)
+                            : launch_bn(syncbn_bwd_kernel<T, 16, true, true>, &p, p.g, nstream, s);
+            return fold ? launch_bn(syncbn_bwd_kernel<T, 24, false, true>, &p, p.g, nstream, s)
+                        : launch_bn(syncbn_bwd_kernel<T, 16, false, true>, &p, p.g, nstream, s);
+        }
         if (xmask)
             return fold ? launch_bn(syncbn_bwd_kernel<T, 24, true>, &p, p.g, nstream, s)
                         : launch_bn(syncbn_bwd_kernel<T, 16, true>, &p, p.g, nstream, s);

@@ -27,6 +27,8 @@ FORCE_LOCAL = False         # bench.py roofline replay: run single-rank (no exch
 # EXPERIMENTAL (written without access to a GPU; off until measured and parity-checked on hardware, then it becomes
 # the default): BN+ReLU layers without a residual re-derive the ReLU mask from x in the backward instead of reading y
 MASK_FROM_X = os.environ.get("SOD_BN_MASK_FROM_X", "0") == "1"
+# EXPERIMENTAL, same status: L2 eviction-priority hints on the backward's bulk copies
+L2_HINTS = os.environ.get("SOD_BN_L2_HINTS", "0") == "1"
 TRACE: list | None = None   # bench.py: when a list, every forward call appends (n, c, h, w, has_pre, has_res, relu)
 
 
@@ -162,6 +164,8 @@ def raw_backward(dy, x, pre, y, weight, mean, invstd, relu: bool, want_dres: boo
         flags = DEBUG_FLAGS
     if MASK_FROM_X and relu and not want_dres and bias is not None:
         flags |= _lib.SOD_BN_BWD_MASK_FROM_X
+    if L2_HINTS:
+        flags |= _lib.SOD_BN_L2_HINTS
     ws, seq, epoch, cref, soff = _next_call(x.device)
     rc = _lib.lib().sod_syncbn_bwd(
         dy.data_ptr(), x.data_ptr(), pre.data_ptr() if pre is not None else None,

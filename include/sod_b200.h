@@ -119,7 +119,9 @@ enum { SOD_SGD_ZERO_GRAD = 1, SOD_ALGO_NO_MULTIMEM = 2,
        SOD_ALGO_FORCE_MULTIMEM = 16 /* use NVLS even at world 2, where the default is peer loads */,
        SOD_BN_BWD_MASK_FROM_X = 32 /* syncbn_bwd, EXPERIMENTAL (off by default in the host layer until it has been
                                       measured on hardware): re-derive the ReLU mask from x with the forward's
-                                      arithmetic instead of reading y; needs relu, beta and dres == NULL */ };
+                                      arithmetic instead of reading y; needs relu, beta and dres == NULL */,
+       SOD_BN_L2_HINTS = 64 /* syncbn_bwd, EXPERIMENTAL (off by default, as above): L2 eviction-priority hints on the
+                               bulk copies — evict-last for chunks that are fetched twice, evict-first for last uses */ };
 
 int sod_sgd_momentum(float* param, float* mom, float* grad, void* grad16, void* shadow16, int64_t n,
                      const sod_sgd_segment* segs, int nseg, float inv_scale, const uint32_t* found_inf, int flags,

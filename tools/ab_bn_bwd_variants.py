@@ -4,7 +4,7 @@ default on every BN+ReLU-without-residual layer shape of the TestModel (bs 16, 3
 Each launch alone, L2 flushed (CUDA events).  Also checks the two variants against each other: the ReLU mask is
 re-derived from x with the forward's arithmetic, so dz may differ only by the summation order of the statistics.
 
-    python tools/ab_mask_from_x.py            → one JSON line per shape + totals
+    python tools/ab_bn_bwd_variants.py            → one JSON line per shape + totals
 """
 import json
 import os
@@ -38,7 +38,8 @@ def timeit(fn, iters=7):
     return sorted(ts)[len(ts) // 2]
 
 
-tot = {"default_us": 0.0, "xmask_us": 0.0, "other_us": 0.0}
+VARIANTS = [("default", False, False), ("xmask", True, False), ("hints", False, True), ("xmask_hints", True, True)]
+tot = {name: 0.0 for name, _, _ in VARIANTS}
 for (n, c, h, w, has_pre, has_res, relu), count in sorted(uniq.items(), key=lambda kv: -kv[0][0] * kv[0][1] * kv[0][2] * kv[0][3]):
     mk = lambda: torch.randn((n, c, h, w), device="cuda", dtype=dtype).contiguous(memory_format=torch.channels_last)  # noqa: E731
     x, dy = mk(), mk()
@@ -53,28 +54,26 @@ for (n, c, h, w, has_pre, has_res, relu), count in sorted(uniq.items(), key=lamb
     _, _, _, _, mean, invstd = y.grad_fn.saved_tensors          # (x, pre, y|None, weight, mean, invstd) of _SyncBNFn
     weight, bias = bn.weight.detach(), bn.bias.detach()
     args = (dy, x, pre, y.detach() if relu else None, weight, mean, invstd, relu, has_res)
-    syncbn.MASK_FROM_X = False
-    d_us = timeit(lambda: raw_backward(*args, bias=bias))
-    dz0, _, dg0, db0 = raw_backward(*args, bias=bias)
+    eligible = relu and not has_res
     rec = dict(shape=[n, c, h, w], pre=has_pre, res=has_res, relu=relu, count=count, MB=round(2 * n * c * h * w / 1e6, 2),
-               default_us=round(d_us, 1))
-    if relu and not has_res:
-        syncbn.MASK_FROM_X = True
-        x_us = timeit(lambda: raw_backward(*args, bias=bias))
-        dz1, _, dg1, db1 = raw_backward(*args, bias=bias)
-        syncbn.MASK_FROM_X = False
-        scale = float(dz0.float().abs().max())
-        rec.update(xmask_us=round(x_us, 1), speedup=round(d_us / x_us, 3),
-                   dz_max_rel=float((dz0.float() - dz1.float()).abs().max()) / max(scale, 1e-12),
-                   dz_mismatch_frac=float((dz0 != dz1).float().mean()),
-                   dgamma_max_rel=float(((dg0 - dg1).abs() / (dg0.abs() + 1e-3)).max()),
-                   dbeta_max_rel=float(((db0 - db1).abs() / (db0.abs() + 1e-3)).max()))
-        tot["default_us"] += d_us * count
-        tot["xmask_us"] += x_us * count
-    else:
-        tot["other_us"] += d_us * count
+               xmask_eligible=eligible)
+    ref = None
+    for name, xm, hints in VARIANTS:
+        syncbn.MASK_FROM_X, syncbn.L2_HINTS = xm and eligible, hints
+        try:
+            us = timeit(lambda: raw_backward(*args, bias=bias))
+            dz, _, dg, db = raw_backward(*args, bias=bias)
+            torch.cuda.synchronize()
+        finally:
+            syncbn.MASK_FROM_X, syncbn.L2_HINTS = False, False
+        rec[name + "_us"] = round(us, 1)
+        tot[name] += us * count
+        if ref is None:
+            ref = (dz.float(), dg.clone(), db.clone())
+        else:
+            scale = max(float(ref[0].abs().max()), 1e-12)
+            rec[name + "_dz_max_rel"] = float((ref[0] - dz.float()).abs().max()) / scale
+            rec[name + "_dgamma_max_rel"] = float(((ref[1] - dg).abs() / (ref[1].abs() + 1e-3)).max())
     print(json.dumps(rec), flush=True)
-print(json.dumps({"eligible_layers_default_us": round(tot["default_us"]), "eligible_layers_xmask_us": round(tot["xmask_us"]),
-                  "other_layers_us": round(tot["other_us"]),
-                  "bwd_total_default_us": round(tot["default_us"] + tot["other_us"]),
-                  "bwd_total_with_xmask_us": round(tot["xmask_us"] + tot["other_us"])}))
+print(json.dumps({"bwd_total_us": {k: round(v) for k, v in tot.items()},
+                  "note": "84 launches per iteration, each alone with L2 flushed; xmask applies to the eligible layers only"}))
