@@ -7,6 +7,8 @@ the parity tests and `__graft_entry__.smoke()` all drive, so the measured path i
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib, amp, comm, network, syncbn
@@ -15,6 +17,9 @@ from .optim import CustomScheduler, make_optimizer
 from .parallel import DistributedDataParallel
 from .syncbn import convert_syncbn_model
 from .utils import init_seed
+
+# EXPERIMENTAL: overlap the next batch's host→device copy with the running iteration (see Trainer._stage_inputs)
+PREFETCH_H2D = os.environ.get("SOD_E2E_PREFETCH", "0") == "1"
 
 
 class Trainer:
@@ -154,9 +159,12 @@ class Trainer:
         """end-to-end form: pinned host batch → device (train.py:291-292) → iteration → loss back to pinned host
         memory.  The D2H read is asynchronous; `last_loss()` waits for it."""
         if self.use_graph and self._graph is not None and tuple(x_pinned.shape) == self._graph_key[0]:
-            # H2D straight into the graph's static inputs
-            self._static_x.copy_(x_pinned, non_blocking=True)
-            self._static_m.copy_(m_pinned, non_blocking=True)
+            if PREFETCH_H2D:
+                self._stage_inputs(x_pinned, m_pinned)
+            else:
+                # H2D straight into the graph's static inputs
+                self._static_x.copy_(x_pinned, non_blocking=True)
+                self._static_m.copy_(m_pinned, non_blocking=True)
             self._graph.replay()
             self.optimizer.steps += 1
             _lib.count_launch(self._graph_launches)
@@ -168,6 +176,34 @@ class Trainer:
         self._pinned_loss.copy_(reduced.reshape(1), non_blocking=True)
         self._loss_event = torch.cuda.Event()
         self._loss_event.record()
+
+    def _stage_inputs(self, x_pinned: torch.Tensor, m_pinned: torch.Tensor) -> None:
+        """EXPERIMENTAL (PREFETCH_H2D, off until validated on hardware): the H2D copy of this call's batch runs on a copy
+        stream into one of two staging buffers, so it overlaps the previous call's iteration (the host loop runs ahead:
+        nothing in `step_from_host` blocks); the iteration's stream then only pays a device-to-device copy into the
+        graph's static inputs.  Same contract as the plain path: every step's H2D and D2H stay inside the caller's
+        timed region.  (The reference prefetches too: `BackgroundGenerator(tr_loader, max_prefetch=2)`, train.py:278-285.)"""
+        if getattr(self, "_copy_stream", None) is None or self._stage[0][0].shape != self._static_x.shape:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._stage = [(torch.empty_like(self._static_x), torch.empty_like(self._static_m)) for _ in range(2)]
+            self._stage_ready = [torch.cuda.Event(), torch.cuda.Event()]     # H2D into stage k has finished
+            self._stage_free = [None, None]                                  # the D2D out of stage k has finished
+            self._stage_idx = 0
+        k = self._stage_idx
+        self._stage_idx ^= 1
+        cs, main = self._copy_stream, torch.cuda.current_stream()
+        if self._stage_free[k] is not None:
+            cs.wait_event(self._stage_free[k])
+        with torch.cuda.stream(cs):
+            self._stage[k][0].copy_(x_pinned, non_blocking=True)
+            self._stage[k][1].copy_(m_pinned, non_blocking=True)
+            self._stage_ready[k].record(cs)
+        main.wait_event(self._stage_ready[k])
+        self._static_x.copy_(self._stage[k][0])
+        self._static_m.copy_(self._stage[k][1])
+        free = torch.cuda.Event()
+        free.record(main)
+        self._stage_free[k] = free
 
     def last_loss(self) -> float:
         if self._loss_event is not None:
