@@ -204,17 +204,18 @@ def bn_roofline(trace, dtype, iters=5):
         # (SURVEY §8d's 10 B/elem assumed two passes over dy,x; the kernel keeps its strip in shared memory between
         # the reduction and the elementwise phase, so the honest denominator is the single-pass figure: 6 B/elem
         # for plain bf16 backward, +2 B/elem per fused operand)
-        reads = 2 + (1 if has_pre else 0) + (1 if relu else 0)
+        from_x = _sbn.MASK_FROM_X and relu and not has_res        # experimental variant: y is not read at all
+        reads = 2 + (1 if has_pre else 0) + (1 if relu and not from_x else 0)
         byts = (reads + 1 + (1 if has_res else 0)) * esz * elems
-        layers.append(((dy, x, pre, y, weight, mean, invstd, relu, has_res), byts))
+        layers.append(((dy, x, pre, y, weight, mean, invstd, relu, has_res), dict(bias=torch.zeros(c, device="cuda")), byts))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     total_ms, total_bytes = 0.0, 0
     for it in range(iters + 1):
-        for (a, byts) in layers:
+        for (a, kw, byts) in layers:
             flush.zero_()
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-            raw_backward(*a)                       # exactly one sod_syncbn_bwd launch
+            raw_backward(*a, **kw)                 # exactly one sod_syncbn_bwd launch
             e.record()
             e.synchronize()
             if it > 0:
