@@ -181,6 +181,13 @@ __device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gmem_s
         "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
         : "memory");
 }
+constexpr uint64_t kL2EvictNormal = 0x1000000000000000ull;
+// 16-byte global store with an L2 eviction-priority hint
+__device__ __forceinline__ void st16_hint(void* p, uint4 v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w),
+                 "l"(policy)
+                 : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0;

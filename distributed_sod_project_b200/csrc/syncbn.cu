@@ -30,6 +30,8 @@
 // world == 1 uses the same packet mechanism for the intra-GPU broadcast, so there is no grid barrier.
 // All CTAs must be co-resident (grid ≤ #SMs, 1 CTA/SM). Every spin is bounded; a timeout sets
 // comm->error_flag and lets the kernel run to completion (outstanding bulk copies must land).
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace sod {
@@ -104,6 +106,7 @@ struct BnBwd {
     const uint32_t* epoch;
     int use_mc;
     const float* beta;            // XMASK only: the ReLU mask is recomputed from x (y is not read)
+    uint64_t store_policy;        // HINT only: L2 policy of the dz / dres stores
 };
 
 // folded conv bias of the 8 channels a thread owns (fp32 master or bf16 shadow leaves)
@@ -629,6 +632,28 @@ __global__ void __launch_bounds__(kBlock, 1) syncbn_fwd_kernel(const __grid_cons
 // =================================================================================================
 // backward
 // =================================================================================================
+// 8 values → element type → 16-byte stores carrying an L2 policy (HINT variants only)
+template <typename T>
+__device__ __forceinline__ void store8_hint(T* p, const float (&f)[8], uint64_t policy) {
+    if constexpr (sizeof(T) == 4) {
+        st16_hint(p, make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3])), policy);
+        st16_hint(p + 4, make_uint4(__float_as_uint(f[4]), __float_as_uint(f[5]), __float_as_uint(f[6]), __float_as_uint(f[7])), policy);
+    } else {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+                const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+                w[i] = *reinterpret_cast<const uint32_t*>(&h);
+            } else {
+                const __half2 h = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+                w[i] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+        }
+        st16_hint(p, make_uint4(w[0], w[1], w[2], w[3]), policy);
+    }
+}
+
 // XMASK (experimental, SOD_BN_BWD_MASK_FROM_X): a BN+ReLU layer without residual does not stream y at all — the
 // mask y > 0 is re-derived from x with the forward's own arithmetic (y = fma(z, invstd*γ, fma(b, invstd*γ, β - mean*invstd*γ)),
 // same operations in the same order, so the sign agrees with the stored y except where |y| is denormal).  One stream
@@ -819,11 +844,15 @@ __global__ void __launch_bounds__(kBlock, 1) syncbn_bwd_kernel(const __grid_cons
         for (int q = tid; q < npk; q += kThreads) {
             float d[8], z[8];
             load_packet(s, q, d, z);
-            if (gdres) IO<T>::store8(gdres + ebase + static_cast<size_t>(q) * 8, d);
+            if (gdres) {
+                if (HINT) store8_hint(gdres + ebase + static_cast<size_t>(q) * 8, d, prm.store_policy);
+                else IO<T>::store8(gdres + ebase + static_cast<size_t>(q) * 8, d);
+            }
             float o[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) o[k] = fmaf(A[k], d[k], fmaf(B[k], z[k], D[k]));
-            IO<T>::store8(gdz + ebase + static_cast<size_t>(q) * 8, o);
+            if (HINT) store8_hint(gdz + ebase + static_cast<size_t>(q) * 8, o, prm.store_policy);
+            else IO<T>::store8(gdz + ebase + static_cast<size_t>(q) * 8, o);
         }
         const int stage_load = streamed ? kload : nres0 + u;
         if (stage_load + NS < total_loads) ring.release(s);
@@ -991,6 +1020,11 @@ extern "C" int sod_syncbn_bwd(const void* dy, const void* x, const void* pre_add
     if (bn_ws_layout(channels, &p.w, workspace) > workspace_bytes) return SOD_EWORKSPACE;
     p.dy = dy; p.x = x; p.pre = pre_add; p.y = (relu && !xmask) ? y : nullptr; p.dz = dz; p.dres = dres;
     p.beta = beta;
+    {   // HINT: a layer whose operands cannot all sit in L2 anyway writes its outputs evict-first, so that the part of the
+        // strip phase 2 still has to fetch is not pushed out by them; a small layer keeps its outputs for the consumer
+        const long long footprint = static_cast<long long>(rows) * channels * (dtype == SOD_F32 ? 4 : 2) * (nstream + 1 + (dres ? 1 : 0));
+        p.store_policy = footprint > (96ll << 20) ? kL2EvictFirst : kL2EvictNormal;
+    }
     p.gamma = gamma; p.smean = save_mean; p.sinvstd = save_invstd; p.dgamma = dgamma; p.dbeta = dbeta;
     p.relu = relu; p.stats_off = stats_off; p.tag = seq; p.epoch = epoch;
     p.accumulate = (flags & SOD_BN_ACCUMULATE_PARAM_GRADS) ? 1 : 0;
