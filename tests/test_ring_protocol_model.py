@@ -89,3 +89,19 @@ def test_ring_protocol_training(NS):
 def test_ring_protocol_eval(NS):
     for n in range(1, 40):
         assert simulate(n, NS, training=False) == n
+
+
+@pytest.mark.parametrize("NS", [2, 3, 4, 7, 16])
+def test_l2_hint_classification(NS):
+    """producer_loop<…, HINT>: a load is issued evict-last iff that chunk is loaded a second time later; every other load
+    (chunks that stay resident, and the second loads themselves) is a last use and goes evict-first"""
+    for n in range(1, 60):
+        nres0 = max(n - NS, 0)
+        total = n + nres0
+        seq = [load_chunk_of(k, n, nres0) for k in range(total)]
+        for k, chunk in enumerate(seq):
+            again_formula = k < n and k < nres0                    # csrc/syncbn.cu producer_loop
+            again_truth = chunk in seq[k + 1:]
+            assert again_formula == again_truth, (n, NS, k, chunk)
+        # every chunk is loaded at most twice, and the second load is never marked for keeping
+        assert all(seq.count(c) <= 2 for c in set(seq))
