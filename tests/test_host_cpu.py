@@ -219,3 +219,24 @@ def test_ctypes_prototypes_match_header_argument_by_argument():
                 assert b is C.c_void_p or (isinstance(b, type) and issubclass(b, C._Pointer)), f"{name} arg {i}: {b} for a pointer"
             else:
                 assert k is b or k == b, f"{name} arg {i}: header {k}, binding {b}"
+
+
+def test_amp_seam_call_shapes():
+    """apex-amp call shapes the reference uses (train.py:183, 299; utils/pipeline_ops.py:74,121)"""
+    from distributed_sod_project_b200 import _lib, amp
+    saved = dict(amp._cfg)
+    try:
+        net = nn.Conv2d(3, 4, 1)
+        opt = torch.optim.SGD(net.parameters(), lr=0.1)
+        m, o = amp.initialize(net, opt, opt_level="O1")                 # (model, optimizer) like apex
+        assert m is net and o is opt
+        assert amp.initialize(nn.Conv2d(3, 4, 1), opt_level="O0") is not None          # model only → model only
+        with pytest.raises(_lib.SodError):
+            amp.initialize(net, opt, opt_level="O2")
+        loss = torch.tensor(2.0, requires_grad=True)
+        with amp.scale_loss(loss, opt) as scaled:                      # bf16: static scale 1 → the loss itself
+            assert scaled is loss
+        amp.load_state_dict({"loss_scaler0": {"loss_scale": 1024.0, "unskipped": 7}})
+        assert amp.state_dict() == {"loss_scaler0": {"loss_scale": 1024.0, "unskipped": 7}}
+    finally:
+        amp._cfg.clear(); amp._cfg.update(saved)
