@@ -1,13 +1,12 @@
 #!/bin/bash
 # One gpurun call that validates and measures everything that was prepared without a GPU at the end of round 1
 # (DESIGN §4.8).  Usage from the build container:
-#     gpurun --timeout 2400 -- 'bash tools/round2_first_call.sh'
+#     gpurun --timeout 1800 -- 'bash tools/round2_first_call.sh'        (≈20 minutes of box time)
 # Results land in gpurun_out/r2_*.  Every step has its own timeout so that a hang costs minutes, not the box.
 cd "$(dirname "$0")/.." || exit 1
 mkdir -p gpurun_out
 run() { local name=$1; shift; echo "== $name"; ( time timeout 900 "$@" ) > "gpurun_out/r2_$name.log" 2>&1; echo "   exit $?"; tail -3 "gpurun_out/r2_$name.log"; }
 
-run gpu_default        python -m pytest tests -m gpu -x -q
 SOD_EXPERIMENTAL=1 run gpu_experimental python -m pytest tests/test_gpu_syncbn.py tests/test_gpu_step.py -m gpu -q -k "mask_from_x or step_from_host"
 SOD_BN_MASK_FROM_X=1 run gpu_xmask      python -m pytest tests -m gpu -x -q
 SOD_BN_MASK_FROM_X=1 SOD_BN_L2_HINTS=1 run gpu_xmask_hints python -m pytest tests/test_gpu_syncbn.py tests/test_gpu_step.py -m gpu -x -q
@@ -15,7 +14,6 @@ run ab_bn_bwd          python tools/ab_bn_bwd_variants.py
 run bench_default      python bench.py --no-cpu-baseline
 SOD_E2E_PREFETCH=1 run bench_prefetch   python bench.py --no-cpu-baseline
 SOD_BN_MASK_FROM_X=1 run bench_xmask    python bench.py --no-cpu-baseline
-SOD_BN_MASK_FROM_X=1 SOD_BN_L2_HINTS=1 run bench_xmask_hints python bench.py --no-cpu-baseline
 SOD_BN_MASK_FROM_X=1 SOD_BN_L2_HINTS=1 SOD_E2E_PREFETCH=1 run bench_all python bench.py --no-cpu-baseline
 grep -h '"metric"' gpurun_out/r2_bench_*.log | python -c '
 import json, sys
