@@ -287,6 +287,8 @@ def run_b200_arm(args):
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     args.warmup = max(3, args.warmup)          # timing rule: at least 3 warm-up iterations
     torch.backends.cudnn.benchmark = True
+    if os.environ.get("SOD_CUDNN_BENCH_LIMIT"):      # experiment knob: 0 = let cuDNN's autotuner try every engine (default 10)
+        torch.backends.cudnn.benchmark_limit = int(os.environ["SOD_CUDNN_BENCH_LIMIT"])
     log('building trainer')
     if args.impl == "torch":
         tr = TorchEagerTrainer(args.model, dtype)

@@ -14,6 +14,7 @@ run ab_bn_bwd          python tools/ab_bn_bwd_variants.py
 run bench_default      python bench.py --no-cpu-baseline
 SOD_E2E_PREFETCH=1 run bench_prefetch   python bench.py --no-cpu-baseline
 SOD_BN_MASK_FROM_X=1 run bench_xmask    python bench.py --no-cpu-baseline
+SOD_CUDNN_BENCH_LIMIT=0 run bench_cudnn_all_engines python bench.py --no-cpu-baseline
 SOD_BN_MASK_FROM_X=1 SOD_BN_L2_HINTS=1 SOD_E2E_PREFETCH=1 run bench_all python bench.py --no-cpu-baseline
 grep -h '"metric"' gpurun_out/r2_bench_*.log | python -c '
 import json, sys
