@@ -163,6 +163,15 @@ class _Stem(nn.Sequential):
         return bn_act(self[1], self[0](x))
 
 
+class _StemPool(nn.MaxPool2d):
+    """the ResNet stem's MaxPool2d(3, 2, 1); routed to csrc/maxpool.cu when that (experimental) kernel is enabled"""
+
+    def forward(self, x):
+        from .. import resample
+        y = resample.maxpool3x3s2(x) if (self.kernel_size, self.stride, self.padding, self.dilation, self.ceil_mode) == (3, 2, 1, 1, False) else None
+        return y if y is not None else super().forward(x)
+
+
 _RESNET50_STAGES = ((64, 3, 1), (128, 4, 2), (256, 6, 2), (512, 3, 2))  # (width, blocks, stride)
 
 
@@ -175,7 +184,7 @@ def resnet50_stages() -> tuple[nn.Module, nn.Module, nn.Module, nn.Module, nn.Mo
     """
     stem_conv = nn.Conv2d(3, 64, 7, 2, 3, bias=False)
     stem = _Stem(stem_conv, nn.BatchNorm2d(64), nn.ReLU(inplace=True))
-    pool = nn.MaxPool2d(3, 2, 1)
+    pool = _StemPool(3, 2, 1)
 
     layers, cin = [], 64
     for width, depth, stride in _RESNET50_STAGES:

@@ -7,11 +7,15 @@ returns None so the caller keeps the torch op — those are shapes the TestModel
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
 
 ENABLED = False     # switched on by the B200 engine (engine.Trainer)
+# EXPERIMENTAL: the stem's MaxPool2d(3, 2, 1) through csrc/maxpool.cu — off until checked against torch on hardware
+MAXPOOL_ENABLED = os.environ.get("SOD_MAXPOOL", "0") == "1"
 
 
 def _ok(x: torch.Tensor) -> bool:
@@ -93,3 +97,39 @@ def avgpool2x2(x: torch.Tensor) -> torch.Tensor | None:
     if not _ok(x) or x.shape[2] % 2 or x.shape[3] % 2:
         return None
     return _AvgPool2x2.apply(x)
+
+
+class _MaxPool3x3s2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _rows(x)
+        n, c, h, w = x.shape
+        ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        y = torch.empty((n, c, ho, wo), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+        arg = torch.empty(n * ho * wo * c, dtype=torch.uint8, device=x.device)      # window position kh*3+kw per element
+        rc = _lib.lib().sod_maxpool3x3s2_fwd(x.data_ptr(), y.data_ptr(), arg.data_ptr(), n, h, w, c, _lib.dtype_code(x.dtype),
+                                             _lib.stream_ptr())
+        _lib.check(rc, "sod_maxpool3x3s2_fwd")
+        _lib.count_launch()
+        ctx.shape = (n, c, h, w)
+        ctx.save_for_backward(arg)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (arg,) = ctx.saved_tensors
+        n, c, h, w = ctx.shape
+        dy = _rows(dy)
+        dx = torch.empty((n, c, h, w), dtype=dy.dtype, device=dy.device, memory_format=torch.channels_last)
+        rc = _lib.lib().sod_maxpool3x3s2_bwd(dy.data_ptr(), arg.data_ptr(), dx.data_ptr(), n, h, w, c, _lib.dtype_code(dy.dtype),
+                                             _lib.stream_ptr())
+        _lib.check(rc, "sod_maxpool3x3s2_bwd")
+        _lib.count_launch()
+        return dx
+
+
+def maxpool3x3s2(x: torch.Tensor) -> torch.Tensor | None:
+    """MaxPool2d(3, stride 2, padding 1); None (caller keeps the torch op) unless the experimental kernel is enabled"""
+    if not (MAXPOOL_ENABLED and _ok(x)):
+        return None
+    return _MaxPool3x3s2.apply(x)

@@ -191,6 +191,15 @@ int sod_upsample2x_bilinear_bwd(const void* dy, void* dx, int n, int h, int w, i
 int sod_avgpool2x2_fwd(const void* x, void* y, int n, int h_out, int w_out, int c, int dtype, void* stream);
 int sod_avgpool2x2_bwd(const void* dy, void* dx, int n, int h_out, int w_out, int c, int dtype, void* stream);
 
+/* EXPERIMENTAL (exported, but the host layer keeps it off until it has been checked against torch on hardware):
+ * MaxPool2d(kernel 3, stride 2, padding 1) of the ResNet stem (backbone/origin/resnet.py `maxpool`; `div_4` in
+ * backbone/origin/from_origin.py:7-15), channels-last [N,H,W,C], C % 8 == 0; (h, w) = INPUT size, output
+ * ((h-1)/2+1, (w-1)/2+1).  argmax: one byte per OUTPUT element (window position kh*3+kw), written by the forward and
+ * read by the backward, which is a deterministic gather with fp32 accumulation.  Ties / NaN as torch: first maximum
+ * in (kh, kw) scan order, NaN propagates. */
+int sod_maxpool3x3s2_fwd(const void* x, void* y, void* argmax, int n, int h, int w, int c, int dtype, void* stream);
+int sod_maxpool3x3s2_bwd(const void* dy, const void* argmax, void* dx, int n, int h, int w, int c, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -74,3 +74,36 @@ def test_unsupported_shapes_fall_back_and_backward_is_deterministic():
         resample.upsample2x(xs, (40, 40)).backward(dy)
         grads.append(xs.grad.clone())
     assert torch.equal(grads[0], grads[1]) and torch.equal(grads[0], grads[2])
+
+
+@pytest.mark.skipif(__import__("os").environ.get("SOD_EXPERIMENTAL") != "1",
+                    reason="experimental kernel (not yet validated on hardware): run with SOD_EXPERIMENTAL=1")
+@pytest.mark.parametrize("shape", [(16, 64, 160, 160), (2, 8, 9, 7), (3, 32, 1, 1), (2, 64, 2, 5), (4, 16, 13, 16)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("ties", [False, True])
+def test_maxpool3x3s2_matches_torch(shape, dtype, ties):
+    """csrc/maxpool.cu against F.max_pool2d(3, 2, 1): forward bit-exact (incl. which element wins a tie, through the
+    backward), backward equal up to the rounding of ≤4-term fp32 sums"""
+    from distributed_sod_project_b200 import resample
+    x1 = _mk(shape, dtype, 5)
+    if ties:
+        x1 = (x1 * 2).round() / 2                      # many equal maxima inside a window
+    x1 = x1.requires_grad_(True)
+    x2 = x1.detach().clone().requires_grad_(True)
+    y1 = resample._MaxPool3x3s2.apply(x1)
+    y2 = F.max_pool2d(x2, 3, 2, 1)
+    assert y1.shape == y2.shape and torch.equal(y1, y2)
+    dy = _mk(tuple(y2.shape), dtype, 6)
+    y1.backward(dy)
+    y2.backward(dy)
+    torch.cuda.synchronize()
+    tol = dict(rtol=1e-6, atol=1e-6) if dtype == torch.float32 else dict(rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(x1.grad.float(), x2.grad.float(), **tol)
+    # the routed module: identical to nn.MaxPool2d when the switch is on
+    from distributed_sod_project_b200.network import blocks
+    old, resample.MAXPOOL_ENABLED = resample.MAXPOOL_ENABLED, True
+    try:
+        if shape[1] % 8 == 0:
+            assert torch.equal(blocks._StemPool(3, 2, 1)(x1.detach()), y2.detach())
+    finally:
+        resample.MAXPOOL_ENABLED = old
