@@ -18,8 +18,9 @@ from .parallel import DistributedDataParallel
 from .syncbn import convert_syncbn_model
 from .utils import init_seed
 
-# EXPERIMENTAL: overlap the next batch's host→device copy with the running iteration (see Trainer._stage_inputs)
-PREFETCH_H2D = os.environ.get("SOD_E2E_PREFETCH", "0") == "1"
+# overlap the next batch's host→device copy with the running iteration (see Trainer._stage_inputs); validated on B200 in
+# round 2 (profiles/r02_call1_*): e2e 1444 → 1559 img/s.  SOD_E2E_PREFETCH=0 restores the serialized copy.
+PREFETCH_H2D = os.environ.get("SOD_E2E_PREFETCH", "1") == "1"
 
 
 class Trainer:
@@ -178,7 +179,7 @@ class Trainer:
         self._loss_event.record()
 
     def _stage_inputs(self, x_pinned: torch.Tensor, m_pinned: torch.Tensor) -> None:
-        """EXPERIMENTAL (PREFETCH_H2D, off until validated on hardware): the H2D copy of this call's batch runs on a copy
+        """(PREFETCH_H2D, default on) the H2D copy of this call's batch runs on a copy
         stream into one of two staging buffers, so it overlaps the previous call's iteration (the host loop runs ahead:
         nothing in `step_from_host` blocks); the iteration's stream then only pays a device-to-device copy into the
         graph's static inputs.  Same contract as the plain path: every step's H2D and D2H stay inside the caller's

@@ -14,8 +14,8 @@ import torch
 from . import _lib
 
 ENABLED = False     # switched on by the B200 engine (engine.Trainer)
-# EXPERIMENTAL: the stem's MaxPool2d(3, 2, 1) through csrc/maxpool.cu — off until checked against torch on hardware
-MAXPOOL_ENABLED = os.environ.get("SOD_MAXPOOL", "0") == "1"
+# the stem's MaxPool2d(3, 2, 1) through csrc/maxpool.cu (checked against torch on B200 in round 2; SOD_MAXPOOL=0 → torch op)
+MAXPOOL_ENABLED = os.environ.get("SOD_MAXPOOL", "1") == "1"
 
 
 def _ok(x: torch.Tensor) -> bool:

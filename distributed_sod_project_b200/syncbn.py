@@ -24,11 +24,12 @@ from . import _lib, comm
 _state: dict = {}
 DEBUG_FLAGS = 0             # tools/bn_phases.py sets SOD_DEBUG_TIMING (4)
 FORCE_LOCAL = False         # bench.py roofline replay: run single-rank (no exchange) even inside a process group
-# EXPERIMENTAL (written without access to a GPU; off until measured and parity-checked on hardware, then it becomes
-# the default): BN+ReLU layers without a residual re-derive the ReLU mask from x in the backward instead of reading y
-MASK_FROM_X = os.environ.get("SOD_BN_MASK_FROM_X", "0") == "1"
-# EXPERIMENTAL, same status: L2 eviction-priority hints on the backward's bulk copies
-L2_HINTS = os.environ.get("SOD_BN_L2_HINTS", "0") == "1"
+# BN+ReLU layers without a residual re-derive the ReLU mask from x in the backward instead of reading y (one input stream
+# less).  Default on since round 2: per-layer A/B on B200 (profiles/r02_call1_ab_bn_bwd.txt) 2531 → 2231 µs for the 84
+# backward launches together with the L2 hints, dz identical to the y-mask variant.  SOD_BN_MASK_FROM_X=0 turns it off.
+MASK_FROM_X = os.environ.get("SOD_BN_MASK_FROM_X", "1") == "1"
+# L2 eviction-priority hints on the backward's bulk copies (same A/B; SOD_BN_L2_HINTS=0 turns them off)
+L2_HINTS = os.environ.get("SOD_BN_L2_HINTS", "1") == "1"
 TRACE: list | None = None   # bench.py: when a list, every forward call appends (n, c, h, w, has_pre, has_res, relu)
 
 
@@ -151,7 +152,7 @@ def raw_backward(dy, x, pre, y, weight, mean, invstd, relu: bool, want_dres: boo
                  dconv_bias=(None, None), bias=None):
     """one `sod_syncbn_bwd` launch on channels-last tensors; returns (dz, dres|None, dgamma, dbeta).
     `into=(weight_grad, bias_grad)`: accumulate the parameter gradients into those fp32 tensors instead.
-    `bias` (β) is only read by the experimental MASK_FROM_X variant."""
+    `bias` (β) is only read by the MASK_FROM_X variant."""
     n, c, h, w = x.shape
     dz = torch.empty_like(x)
     dres = torch.empty_like(x) if want_dres else None

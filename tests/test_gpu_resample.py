@@ -76,8 +76,6 @@ def test_unsupported_shapes_fall_back_and_backward_is_deterministic():
     assert torch.equal(grads[0], grads[1]) and torch.equal(grads[0], grads[2])
 
 
-@pytest.mark.skipif(__import__("os").environ.get("SOD_EXPERIMENTAL") != "1",
-                    reason="experimental kernel (not yet validated on hardware): run with SOD_EXPERIMENTAL=1")
 @pytest.mark.parametrize("shape", [(16, 64, 160, 160), (2, 8, 9, 7), (3, 32, 1, 1), (2, 64, 2, 5), (4, 16, 13, 16)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("ties", [False, True])

@@ -158,8 +158,6 @@ def test_bf16_shadow_weights_do_not_change_the_trajectory():
     assert float(cos) > 0.9, float(cos)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("SOD_EXPERIMENTAL") != "1",
-                    reason="experimental host path (not yet validated on hardware): run with SOD_EXPERIMENTAL=1")
 @pytest.mark.parametrize("prefetch", [False, True])
 def test_step_from_host_feeds_every_batch(prefetch, monkeypatch):
     """`step_from_host` (bench.py's e2e arm): with and without the staged H2D prefetch, each iteration must consume exactly

@@ -186,8 +186,6 @@ def test_folded_conv_bias(shape, dtype, bdtype, two):
         assert torch.equal(pre.grad, x.grad)
 
 
-@pytest.mark.skipif(os.environ.get("SOD_EXPERIMENTAL") != "1",
-                    reason="experimental kernel variant (not yet validated on hardware): run with SOD_EXPERIMENTAL=1")
 @pytest.mark.parametrize("shape", [(16, 64, 80, 80), (4, 64, 33, 31), (16, 256, 20, 20), (2, 2048, 2, 2), (16, 32, 160, 160)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("with_pre,with_cb", [(False, False), (True, False), (False, True)])
