@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=4)
     ap.add_argument("--sweep", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay of the iteration")
+    ap.add_argument("--multiscale", action="store_true",
+                    help="BASELINE config 4: one size of {256,320,384} per batch (rank-shared RNG), as the reference's multi-scale collate")
+    ap.add_argument("--no-parity-check", action="store_true", help="skip the untimed world>1 parity leg")
     return ap.parse_args()
 
 
@@ -240,20 +243,26 @@ class TorchEagerTrainer:
 
         init_seed(0)
         self.model = getattr(network, model_name)().cuda().to(memory_format=torch.channels_last)
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        if self.world > 1:      # the stock multi-GPU recipe: nn.SyncBatchNorm + DistributedDataParallel over NCCL
+            self.model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(self.model)
         named = list(self.model.named_parameters())
         groups = [{"params": [p for n, p in named if n.startswith("div") and not n.startswith("div_2")], "lr": 0.005},
                   {"params": [p for n, p in named if not n.startswith("div")], "lr": 0.05}]
         self.opt = torch.optim.SGD(groups, momentum=0.9, weight_decay=5e-4, fused=True)
         self.loss_funcs = [torch.nn.BCEWithLogitsLoss(), StockCEL()]
         self.dtype = dtype
-        self.world = 1
         self.model.train()
+        self.net = self.model
+        if self.world > 1:
+            self.net = torch.nn.parallel.DistributedDataParallel(self.model, device_ids=[torch.cuda.current_device()],
+                                                                 gradient_as_bucket_view=True)
         self._pinned = torch.zeros(1).pin_memory()
 
     def forward_backward_update(self, x, m):
         x = x.contiguous(memory_format=torch.channels_last)
         with torch.autocast("cuda", dtype=self.dtype, enabled=self.dtype != torch.float32):
-            preds = self.model(x)
+            preds = self.net(x)
         loss = sum(f(preds.float(), m) for f in self.loss_funcs)
         self.opt.zero_grad(set_to_none=True)
         loss.backward()
@@ -271,6 +280,138 @@ class TorchEagerTrainer:
     @property
     def module(self):
         return self.model
+
+
+# ----------------------------------------------------------------------------------------------------
+# untimed parity leg for world > 1 (runs on the timed processes, after the timed region)
+# ----------------------------------------------------------------------------------------------------
+def parity_check(tr, rank: int, world: int) -> dict:
+    """Cross-rank correctness of the kernels that only exist at world > 1, against torch's NCCL equivalents on the
+    same inputs (reference semantics: apex DDP + SyncBN, train.py:180-185; apex is absent, torch's SyncBatchNorm /
+    all_reduce / SGD are the in-image stand-ins SURVEY §8c names):
+      1. parameters (and the bf16 shadow) bit-identical on all ranks after the timed steps;
+      2. sod_syncbn_fwd/bwd on three layer shapes vs torch.nn.SyncBatchNorm;
+      3. sod_allreduce_sgd on the real gradient bucket vs dist.all_reduce + the SGD-momentum formula;
+      4. at world 2: the fp32 training trajectory vs the reference's golden vectors (tests/golden/step_res50_w2_s128.npz).
+    Every verdict is all-reduced (MIN) so that all ranks agree; the caller exits non-zero on a mismatch."""
+    import numpy as np
+    from distributed_sod_project_b200 import comm
+    from distributed_sod_project_b200.syncbn import SyncBatchNorm
+    dev = torch.device("cuda", torch.cuda.current_device())
+    out: dict = {}
+
+    def agree(flag: bool) -> bool:
+        t = torch.tensor([1 if flag else 0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(int(t.item()))
+
+    def relerr(a, b) -> float:
+        a, b = a.detach().double(), b.detach().double()
+        return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+    flat = tr.optimizer.flat
+    # 1 ---------------------------------------------------------------------------------------------------------
+    ref = flat.param.clone(); dist.broadcast(ref, 0)
+    same = torch.equal(ref, flat.param)
+    if flat.shadow16 is not None:
+        ref16 = flat.shadow16.clone(); dist.broadcast(ref16, 0)
+        same = same and torch.equal(ref16, flat.shadow16)
+    out["params_identical"] = agree(same)
+    # 2 ---------------------------------------------------------------------------------------------------------
+    bn_rows = []
+    ok_bn = True
+    for (shape, dt, tol) in (((16, 64, 80, 80), torch.float32, 2e-4), ((16, 256, 20, 20), torch.float32, 2e-4),
+                             ((16, 2048, 10, 10), torch.float32, 2e-4), ((16, 64, 80, 80), torch.bfloat16, 3e-2)):
+        g = torch.Generator(device="cpu").manual_seed(4242 + rank)
+        c = shape[1]
+        x0 = (torch.randn(shape, generator=g) * (1.0 + 0.5 * rank) + 0.3 * rank).to(dt).to(dev).contiguous(memory_format=torch.channels_last)
+        dy = torch.randn(shape, generator=g).to(dt).to(dev).contiguous(memory_format=torch.channels_last)
+        mine, theirs = SyncBatchNorm(c).to(dev), torch.nn.SyncBatchNorm(c).to(dev)
+        with torch.no_grad():
+            for bn in (mine, theirs):
+                bn.weight.copy_(torch.linspace(0.5, 1.5, c)); bn.bias.copy_(torch.linspace(-0.3, 0.3, c))
+        res = []
+        for bn in (mine, theirs):
+            x = x0.clone().requires_grad_(True)
+            y = bn(x) if bn is theirs else bn.fused_forward(x)
+            y.backward(dy)
+            res.append((y.detach(), x.grad, bn.weight.grad, bn.bias.grad, bn.running_mean.clone(), bn.running_var.clone()))
+        errs = {k: relerr(a, b) for k, a, b in zip(("y", "dx", "dgamma", "dbeta", "running_mean", "running_var"), res[0], res[1])}
+        good = all(v < tol for v in errs.values())
+        ok_bn = ok_bn and good
+        bn_rows.append({"shape": list(shape), "dtype": str(dt).replace("torch.", ""), "tol": tol, **{k: float(f"{v:.3g}") for k, v in errs.items()}})
+    out["syncbn_vs_torch_nccl"] = {"ok": agree(ok_bn), "cases": bn_rows}
+    # 3 ---------------------------------------------------------------------------------------------------------
+    opt = tr.optimizer
+    snap_p, snap_v = flat.param.clone(), flat.mom.clone()
+    snap_s = flat.shadow16.clone() if flat.shadow16 is not None else None
+    g = torch.Generator(device="cpu").manual_seed(777 + rank)
+    grad = (torch.randn(flat.numel, generator=g) * 1e-2).to(dev)
+    opt.gather_momentum()                                   # the reference SGD below needs the full momentum on every rank
+    v_full = flat.mom.clone()
+    opt.zero_grad()                                         # also drops the weight gradients autograd left from the last step
+    flat.grad.copy_(grad)
+    if flat.grad16 is not None:
+        flat.grad16.zero_()
+    gsum = grad.clone(); dist.all_reduce(gsum)
+    gavg = gsum / world
+    exp_p, exp_v = snap_p.clone(), v_full.clone()
+    for grp, (b, e) in zip(opt.param_groups, flat.ranges):
+        if e > b:
+            gg = gavg[b:e] + grp["weight_decay"] * exp_p[b:e]
+            exp_v[b:e] = grp["momentum"] * exp_v[b:e] + gg
+            exp_p[b:e] = exp_p[b:e] - grp["lr"] * exp_v[b:e]
+    torch.cuda.synchronize(); dist.barrier()
+    opt.step()
+    torch.cuda.synchronize()
+    lo, hi = opt.shard_bounds(rank, world)
+    e_p = relerr(flat.param, exp_p)
+    e_v = relerr(flat.mom[lo:hi], exp_v[lo:hi]) if hi > lo else 0.0
+    cleared = float(flat.grad.abs().max()) == 0.0
+    ref = flat.param.clone(); dist.broadcast(ref, 0)
+    ok_sgd = e_p < 1e-5 and e_v < 1e-5 and cleared and torch.equal(ref, flat.param)
+    out["allreduce_sgd_vs_nccl_plus_sgd"] = {"ok": agree(ok_sgd), "elems": flat.numel, "param_relerr": float(f"{e_p:.3g}"),
+                                             "momentum_shard_relerr": float(f"{e_v:.3g}"), "grads_cleared": cleared}
+    with torch.no_grad():                                    # put the training state back
+        flat.param.copy_(snap_p); flat.mom.copy_(snap_v)
+        if snap_s is not None:
+            flat.shadow16.copy_(snap_s)
+    torch.cuda.synchronize(); dist.barrier()
+    # 4 ---------------------------------------------------------------------------------------------------------
+    gpath = os.path.join(ROOT, "tests", "golden", "step_res50_w2_s128.npz")
+    if world == 2 and os.path.exists(gpath):
+        from distributed_sod_project_b200.engine import Trainer
+        from distributed_sod_project_b200.synthetic import synth_batch
+        gold = np.load(gpath)
+        _, bs, size, _ = (int(v) for v in gold["meta"])
+        tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+        torch.backends.cudnn.allow_tf32 = False; torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.benchmark = False
+        try:
+            t2 = Trainer(model_name="res50", dtype=torch.float32, channels_last=True)
+            errs, ok_g = [], True
+            for it in range(2):
+                xb, mb = synth_batch(1234 + rank + 1000 * it, bs, size)
+                o = t2.step(xb.cuda(), mb.cuda())
+                # the reference value is this rank's LOCAL loss; step() returns the rank mean (train.py:306)
+                want = float(np.mean(gold[f"loss{it}"]))
+                e = abs(o["loss"] - want) / abs(want)
+                errs.append(float(f"{e:.3g}"))
+                ok_g = ok_g and e < 1e-3
+                if it == 0:
+                    ref_l = gold["logits0"][rank * bs:(rank + 1) * bs]
+                    le = float(np.abs(o["preds"].float().cpu().numpy() - ref_l).max() / np.abs(ref_l).max())
+                    errs.append(float(f"{le:.3g}"))
+                    ok_g = ok_g and le < 1e-3
+            t2.check_errors()
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = tf32
+        out["golden_w2_fp32"] = {"ok": agree(ok_g), "loss0_logits0_loss1_relerr": errs, "tol": 1e-3}
+    for a in (getattr(tr.model, "arena", None), comm.small_arena()):
+        if a is not None:
+            a.check_error()
+    out["ok"] = all(v.get("ok", True) if isinstance(v, dict) else bool(v) for v in out.values())
+    return out
 
 
 def run_b200_arm(args):
@@ -296,10 +437,28 @@ def run_b200_arm(args):
         tr = Trainer(model_name=args.model, dtype=dtype, channels_last=True, report_items=False, use_graph=not args.no_graph)
     log('trainer built')
     nb = 4
-    host = [synth_batch(1234 + rank + 100 * i, BS, SIZE) for i in range(nb)]
+    if args.multiscale:
+        # BASELINE config 4: the reference's multi-scale collate draws ONE size per batch (utils/dataset.py:125-132,
+        # config.py:58-60 size_list); all ranks draw the same one (shared RNG).  12 resident batches, 4 per size; the
+        # first three steps visit each size once so that the warm-up captures all three graphs.
+        import random as _random
+        sizes = (256, 320, 384)
+        rng = _random.Random(0)
+        order = [0, 1, 2] + [rng.randrange(3) for _ in range(4096)]
+        host = [synth_batch(1234 + rank + 100 * i, BS, sizes[k]) for k in range(3) for i in range(nb)]
+        seen = [0, 0, 0]
+        pick = []
+        for k in order:                       # batch index of step i: next unused batch of the drawn size
+            pick.append(k * nb + seen[k] % nb)
+            seen[k] += 1
+        mean_pixels = sum(sizes[k] ** 2 for k in order[:args.warmup + args.steps][args.warmup:]) / max(args.steps, 1)
+    else:
+        host = [synth_batch(1234 + rank + 100 * i, BS, SIZE) for i in range(nb)]
+        pick = [i % nb for i in range(8192)]
+        mean_pixels = SIZE * SIZE
     host = [(x.pin_memory(), m.pin_memory()) for x, m in host]
     dev = [(x.cuda(non_blocking=True), m.cuda(non_blocking=True)) for x, m in host]
-    h2d = host[0][0].numel() * 4 + host[0][1].numel() * 4
+    h2d = int(BS * mean_pixels * 16)          # 3 image planes + 1 mask plane, fp32
 
     def sync_all():
         torch.cuda.synchronize()
@@ -322,24 +481,27 @@ def run_b200_arm(args):
 
     # -- device-resident arm ---------------------------------------------------------------------------
     clk = ClockSampler(local).__enter__()
-    syncbn.TRACE = []
+    trace_at = 1 if args.multiscale else 0          # the 320x320 iteration (multi-scale warm-up visits 256, 320, 384)
     for i in range(args.warmup):
-        tr.forward_backward_update(*dev[i % nb])
+        if i == trace_at:
+            syncbn.TRACE = []
+        tr.forward_backward_update(*dev[pick[i]])
         torch.cuda.synchronize(); log(f'warmup {i} done')
-        if i == 0:
+        if i == trace_at:
             trace, syncbn.TRACE = syncbn.TRACE, None
     l0 = _lib.launches
     if os.environ.get("SOD_BENCH_PROFILE"):
         from torch.profiler import ProfilerActivity, profile
         with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
             for i in range(2):
-                tr.forward_backward_update(*dev[i % nb])
+                tr.forward_backward_update(*dev[pick[i]])
             torch.cuda.synchronize()
         with open(os.environ["SOD_BENCH_PROFILE"], "w") as f:
             f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90))
     rid = torch.cuda.nvtx.range_start("timed")      # start/end range: process-wide (backward runs on autograd's thread)
     clk.mark()
-    ms = timed(lambda i: tr.forward_backward_update(*dev[i % nb]), args.steps)
+    w0 = args.warmup
+    ms = timed(lambda i: tr.forward_backward_update(*dev[pick[w0 + i]]), args.steps)
     clk.mark()
     torch.cuda.nvtx.range_end(rid)
     clk.__exit__()
@@ -349,19 +511,33 @@ def run_b200_arm(args):
 
     # -- end-to-end arm: pinned host batch in, loss out, every step ------------------------------------
     for i in range(min(args.warmup, 3)):
-        tr.step_from_host(*host[i % nb])
+        tr.step_from_host(*host[pick[i]])
     tr.last_loss()
-    ms_e2e = timed(lambda i: (tr.step_from_host(*host[i % nb]), tr.last_loss() if i == args.steps - 1 else None), args.steps)
+    ms_e2e = timed(lambda i: (tr.step_from_host(*host[pick[w0 + i]]), tr.last_loss() if i == args.steps - 1 else None), args.steps)
     e2e = world * BS * args.steps / (ms_e2e * 1e-3)
     log(f'e2e done: {ms_e2e / args.steps:.2f} ms/step')
     if args.impl == "torch":
         if rank == 0:
             print(json.dumps({"impl": "torch-eager", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
                               "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "dtype": args.dtype,
+                              "config": {"workload": "stock PyTorch on the same GPUs: nn.BatchNorm2d / nn.SyncBatchNorm + "
+                                                     "DistributedDataParallel over NCCL, torch losses, SGD(fused=True), bf16 autocast, "
+                                                     "channels-last" + (", multi-scale {256,320,384}" if args.multiscale else "")},
                               "e2e": {"value": e2e, "unit": UNIT}, "clocks": clk.summary()}), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
         return
-    if tr.world > 1 and hasattr(tr.model, "arena") and tr.model.arena is not None:
-        tr.model.arena.check_error()
+    tr.check_errors()            # device-side barrier / packet time-outs of BOTH arenas (gradient bucket and SyncBN slots)
+
+    # -- untimed parity leg (world > 1): the driver's GPU test box has one GPU, so the cross-rank kernels are checked here,
+    #    on the very processes and parameters that were just timed; a mismatch fails the run (exit code 1) ---------------
+    parity = None
+    if world > 1 and not args.no_parity_check:
+        try:
+            parity = parity_check(tr, rank, world)
+        except Exception as ex:                          # noqa: BLE001
+            parity = {"ok": False, "error": repr(ex)}
 
     # -- measurements that ride along (BASELINE metric also names the all-reduce bus bandwidth); every rank takes part,
     #    nothing in here may prevent the line from being printed -----------------------------------------------------
@@ -390,6 +566,8 @@ def run_b200_arm(args):
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
+        if parity is not None and not parity.get("ok", False):
+            sys.exit(1)
         return
     pk, pk_kind = peaks()
     from distributed_sod_project_b200.syncbn import SyncBatchNorm
@@ -405,7 +583,10 @@ def run_b200_arm(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": f"TestModel {args.model} (ResNet-50 encoder) {SIZE}x{SIZE} bs={BS}/GPU, one training iteration: "
+            "config": {"workload": f"TestModel {args.model} (ResNet-50 encoder) "
+                                   + ("multi-scale {256,320,384} (one size per batch, rank-shared RNG; BASELINE config 4)"
+                                      if args.multiscale else f"{SIZE}x{SIZE}")
+                                   + f" bs={BS}/GPU, one training iteration: "
                                    "fwd (cuDNN convs NHWC + fused SyncBN kernels) + fused BCE/CEL fwd+bwd + bwd + "
                                    "fused (all-reduce+)SGD-momentum", "global_batch": BS * world,
                        "parallelism": f"dp{world}", "l2": "4 rotating input batches; per-iteration working set (>5 GB of "
@@ -436,6 +617,8 @@ def run_b200_arm(args):
     except Exception as ex:                              # noqa: BLE001
         extras["loss_error"] = repr(ex)
     line["extras"] = extras
+    if parity is not None:
+        line["parity_check"] = parity
     if not args.no_cpu_baseline:
         res = cpu_reference(args.model, args.cpu_batch, 6, 1)
         line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -443,6 +626,8 @@ def run_b200_arm(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if parity is not None and not parity.get("ok", False):
+        sys.exit(1)
 
 
 def run_sweep(args):

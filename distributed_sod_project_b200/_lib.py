@@ -19,8 +19,12 @@ SOD_SGD_ZERO_GRAD = 1
 SOD_ALGO_NO_MULTIMEM = 2
 SOD_BN_ACCUMULATE_PARAM_GRADS = 8
 SOD_ALGO_FORCE_MULTIMEM = 16
-SOD_BN_BWD_MASK_FROM_X = 32     # experimental, see include/sod_b200.h
-SOD_BN_L2_HINTS = 64            # experimental, see include/sod_b200.h
+SOD_BN_BWD_MASK_FROM_X = 32
+SOD_BN_L2_HINTS = 64
+SOD_BN_LAUNCH_COOP = 128
+SOD_BN_LAUNCH_PDL = 256
+SOD_GATHER_MAX_ITEMS = 160
+ABI_VERSION = 6
 
 
 class SodError(RuntimeError):
@@ -31,6 +35,10 @@ class sod_comm(C.Structure):
     _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("peer", C.c_uint64 * SOD_MAX_WORLD),
                 ("mc", C.c_uint64), ("arena_bytes", C.c_uint64), ("error_flag", C.c_void_p),
                 ("timeout_cycles", C.c_uint64), ("block_seq", C.c_void_p)]
+
+
+class sod_gather_item(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst_offset", C.c_int64), ("numel", C.c_int64)]
 
 
 class sod_sgd_segment(C.Structure):
@@ -49,9 +57,10 @@ _PROTOTYPES = {
     "sod_scale_by_device_scalar": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
     "sod_comm_flag_bytes": (C.c_size_t, []),
     "sod_sgd_momentum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
-                                   C.POINTER(sod_sgd_segment), C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_void_p]),
+                                   C.POINTER(sod_sgd_segment), C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_void_p]),
     "sod_allreduce_sgd": (C.c_int, [C.POINTER(sod_comm), C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int64,
-                                    C.POINTER(sod_sgd_segment), C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_void_p]),
+                                    C.POINTER(sod_sgd_segment), C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_void_p]),
+    "sod_grad_gather16": (C.c_int, [C.POINTER(sod_gather_item), C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
     "sod_grad_merge_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "sod_grad_nonfinite": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "sod_allreduce_f32": (C.c_int, [C.POINTER(sod_comm), C.c_uint64, C.c_int64, C.c_float, C.c_int, C.c_int, C.c_void_p]),
@@ -70,6 +79,11 @@ _PROTOTYPES = {
     "sod_avgpool2x2_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "sod_avgpool2x2_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "sod_maxpool3x3s2_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "sod_preprocess_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                       C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p]),
+    "sod_saliency_quantize": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "sod_saliency_head": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "sod_saliency_hist": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sod_maxpool3x3s2_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
 }
 
@@ -77,6 +91,7 @@ EXPORTS = tuple(_PROTOTYPES)
 _lib = None
 _lock = threading.Lock()
 launches = 0   # number of kernel-launching C-ABI calls made by this process (bench.py reports it)
+grad_writes = 0   # bumped whenever a kernel of this library adds into a bound .grad (invisible to autograd's version counters)
 
 
 def lib() -> C.CDLL:

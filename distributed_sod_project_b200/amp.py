@@ -17,6 +17,11 @@ import torch
 from . import _lib
 from .optim import FusedSGD
 
+import os
+
+# SOD_STEAL_WGRADS=0: bind every shadow leaf's .grad to the flat buffer (autograd then launches one add per tensor)
+STEAL_WEIGHT_GRADS = os.environ.get("SOD_STEAL_WGRADS", "1") == "1"
+
 _cfg = {"enabled": False, "dtype": torch.bfloat16, "scale": 1.0, "dynamic": False, "good_steps": 0,
         "growth_interval": 2000, "found_inf": None}
 
@@ -35,13 +40,19 @@ def _install_shadow_weights(model, flat) -> int:
         w16 = flat.view16(flat.shadow16, m.weight)
         w16.requires_grad_(m.weight.requires_grad)
         if m.weight.requires_grad:
-            w16.grad = flat.view16(flat.grad16, m.weight)
+            # weights: `.grad` stays None — autograd then keeps cuDNN's wgrad tensor as it is and the fused step
+            # gathers all of them with one launch (no per-parameter accumulate kernel at the end of backward)
+            flat.shadow_leaves.append((w16, flat.offset_of(m.weight), STEAL_WEIGHT_GRADS))
+            if not STEAL_WEIGHT_GRADS:
+                w16.grad = flat.view16(flat.grad16, m.weight)
         m._sod_w16, m._sod_b16 = w16, None
         if m.bias is not None and id(m.bias) in managed:
             b16 = flat.view16(flat.shadow16, m.bias)
             b16.requires_grad_(m.bias.requires_grad)
             if m.bias.requires_grad:
+                # biases: bound view — the SyncBN backward adds the folded-bias gradient straight into it
                 b16.grad = flat.view16(flat.grad16, m.bias)
+                flat.shadow_leaves.append((b16, flat.offset_of(m.bias), False))
             m._sod_b16 = b16
         elif m.bias is not None:
             continue

@@ -28,13 +28,38 @@ def _unwrap(model: nn.Module) -> nn.Module:
     return model.module if hasattr(model, "module") else model
 
 
+def _compact(obj):
+    """detached copies with storage of their own: the live tensors are views into the flat (possibly symmetric-memory)
+    buffers, and torch.save serialises the whole underlying storage of a view"""
+    if isinstance(obj, torch.Tensor):
+        return obj.detach().clone()
+    if isinstance(obj, dict):
+        return type(obj)((k, _compact(v)) for k, v in obj.items())
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_compact(v) for v in obj)
+    return obj
+
+
 def save_checkpoint(model: nn.Module = None, optimizer: Optimizer = None, amp=None, exp_name: str = "", current_epoch: int = 1,
-                    full_net_path: str = "", state_net_path: str = ""):
-    """Full checkpoint (model + optimizer + amp) and the weights-only file, as the reference writes them."""
-    net_state = _unwrap(model).state_dict()
-    torch.save({"arch": exp_name, "epoch": current_epoch, "net_state": net_state, "opti_state": optimizer.state_dict(),
-                "amp_state": amp.state_dict() if amp else None}, full_net_path)
-    torch.save(net_state, state_net_path)
+                    full_net_path: str = "", state_net_path: str = "", write: bool | None = None):
+    """Full checkpoint (model + optimizer + amp) and the weights-only file, as the reference writes them.
+
+    Distributed: EVERY rank must call this (the momentum of `FusedSGD` is sharded over the ranks and `state_dict()`
+    gathers it with collectives); only the rank with `write=True` (default: rank 0) touches the files, and all ranks
+    leave through a barrier so that nobody runs ahead into the next iteration's device-side barriers while rank 0 is
+    still writing."""
+    import torch.distributed as dist
+    distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    if write is None:
+        write = (not distributed) or dist.get_rank() == 0
+    opti_state = optimizer.state_dict()                       # collective when the momentum is sharded
+    if write:
+        net_state = _compact(_unwrap(model).state_dict())
+        torch.save({"arch": exp_name, "epoch": current_epoch, "net_state": net_state, "opti_state": _compact(opti_state),
+                    "amp_state": amp.state_dict() if amp else None}, full_net_path)
+        torch.save(net_state, state_net_path)
+    if distributed:
+        dist.barrier()
 
 
 def resume_checkpoint(model: nn.Module = None, optimizer: Optimizer = None, amp=None, exp_name: str = "", load_path: str = "",

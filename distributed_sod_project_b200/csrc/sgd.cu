@@ -48,6 +48,13 @@ static int make_seg_table(const sod_sgd_segment* segs, int nseg, int64_t n, SegT
 }
 
 // segment cursor: indices visited by one thread only ever increase
+// learning rate of segment s: from device memory when the host passed a table (a captured CUDA graph then follows
+// the scheduler without being re-captured: reference utils/pipeline_ops.py:225-229 rewrites param_groups[i]["lr"]
+// every epoch or every iteration), else the by-value copy
+__device__ __forceinline__ float seg_lr(const SegTable& t, const float* lr_dev, int s) {
+    return lr_dev != nullptr ? __ldg(lr_dev + s) : t.lr[s];
+}
+
 struct SegCursor {
     int s = 0;
     __device__ __forceinline__ bool find(const SegTable& t, long long vec) {
@@ -83,7 +90,8 @@ __global__ void __launch_bounds__(kThreads) sgd_local_kernel(float4* __restrict_
                                                              float4* __restrict__ g, uint2* __restrict__ g16,
                                                              uint2* __restrict__ shadow, long long nvec,
                                                              const __grid_constant__ SegTable segs, float inv_scale,
-                                                             const uint32_t* found_inf, int zero_grad) {
+                                                             const uint32_t* found_inf, int zero_grad,
+                                                             const float* __restrict__ lr_dev) {
     const bool skip = (found_inf != nullptr && *found_inf != 0);  // amp overflow: no update, but still clear g
     SegCursor cur;
     const long long stride = static_cast<long long>(gridDim.x) * kThreads;
@@ -115,7 +123,7 @@ __global__ void __launch_bounds__(kThreads) sgd_local_kernel(float4* __restrict_
                 if (sidx[u] >= 0) {
                     const int s = sidx[u];
                     const float4 gs = make_float4(gv[u].x * inv_scale, gv[u].y * inv_scale, gv[u].z * inv_scale, gv[u].w * inv_scale);
-                    sgd_update(pv[u], vv[u], gs, segs.lr[s], segs.wd[s], segs.mu[s]);
+                    sgd_update(pv[u], vv[u], gs, seg_lr(segs, lr_dev, s), segs.wd[s], segs.mu[s]);
                     p[i] = pv[u];
                     v[i] = vv[u];
                     if (shadow != nullptr) shadow[i] = f32x4_to_bf16(pv[u]);
@@ -139,6 +147,45 @@ __global__ void grad_merge_bf16_kernel(float4* __restrict__ g, uint2* __restrict
             a.x += h.x; a.y += h.y; a.z += h.z; a.w += h.w;
             g[i] = a;
             g16[i] = make_uint2(0u, 0u);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-tensor gather: the bf16 weight gradients autograd produced (one freshly allocated tensor per
+// parameter) → the flat bf16 gradient buffer, ONE launch instead of one accumulate kernel per tensor
+// ------------------------------------------------------------------------------------------------
+constexpr int kGatherMax = SOD_GATHER_MAX_ITEMS;
+constexpr int kGatherChunk = 8192;          // elements per work unit
+struct GatherTable {
+    int n;
+    const void* src[kGatherMax];
+    unsigned dst_off8[kGatherMax];          // destination offset in units of 8 elements
+    unsigned numel[kGatherMax];
+    unsigned chunk0[kGatherMax + 1];        // prefix sum of ceil(numel / kGatherChunk)
+};
+
+__global__ void __launch_bounds__(256) grad_gather16_kernel(const __grid_constant__ GatherTable t, uint4* __restrict__ dst) {
+    const unsigned total = t.chunk0[t.n];
+    for (unsigned c = blockIdx.x; c < total; c += gridDim.x) {
+        int lo = 0, hi = t.n - 1;           // item with chunk0[item] <= c < chunk0[item+1]
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (t.chunk0[mid] <= c) lo = mid; else hi = mid - 1;
+        }
+        const unsigned first = (c - t.chunk0[lo]) * kGatherChunk;
+        const unsigned left = t.numel[lo] - first;
+        const unsigned cnt = left < kGatherChunk ? left : kGatherChunk;
+        const unsigned short* src = static_cast<const unsigned short*>(t.src[lo]) + first;
+        unsigned short* out = reinterpret_cast<unsigned short*>(dst + t.dst_off8[lo]) + first;
+        if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+            const uint4* s4 = reinterpret_cast<const uint4*>(src);
+            uint4* d4 = reinterpret_cast<uint4*>(out);                 // dst offsets and chunk starts are multiples of 8
+            const unsigned nv = cnt >> 3;
+            for (unsigned i = threadIdx.x; i < nv; i += 256) d4[i] = __ldcs(s4 + i);
+            for (unsigned i = (nv << 3) + threadIdx.x; i < cnt; i += 256) out[i] = src[i];
+        } else {
+            for (unsigned i = threadIdx.x; i < cnt; i += 256) out[i] = src[i];
         }
     }
 }
@@ -183,7 +230,8 @@ __global__ void __launch_bounds__(kThreads) allreduce_sgd_kernel(const __grid_co
                                                                  uint64_t param_off, float4* __restrict__ mom,
                                                                  long long nvec, const __grid_constant__ SegTable segs,
                                                                  float scale, const uint32_t* found_inf,
-                                                                 int zero_grad, uint2* __restrict__ shadow) {
+                                                                 int zero_grad, uint2* __restrict__ shadow,
+                                                                 const float* __restrict__ lr_dev) {
     const bool skip = (found_inf != nullptr && *found_inf != 0);  // caller guarantees identical on all ranks
     // every rank's backward has finished writing its gradients
     if (!comm_block_barrier(c, 0, blockIdx.x)) return;
@@ -210,7 +258,7 @@ __global__ void __launch_bounds__(kThreads) allreduce_sgd_kernel(const __grid_co
                     const int s = cur.s;
                     float4 pv = p_local[i], vv = mom[i];
                     const float4 gs = make_float4(gv[u].x * scale, gv[u].y * scale, gv[u].z * scale, gv[u].w * scale);
-                    sgd_update(pv, vv, gs, segs.lr[s], segs.wd[s], segs.mu[s]);
+                    sgd_update(pv, vv, gs, seg_lr(segs, lr_dev, s), segs.wd[s], segs.mu[s]);
                     mom[i] = vv;
                     broadcast_vec<kMulticast>(c, param_off + static_cast<uint64_t>(i) * 16u, pv);
                 }
@@ -305,8 +353,8 @@ static unsigned comm_grid(long long vecs_per_rank) {
 }  // namespace sod
 
 extern "C" int sod_sgd_momentum(float* param, float* mom, float* grad, void* grad16, void* shadow16, int64_t n,
-                                const sod_sgd_segment* segs, int nseg, float inv_scale, const uint32_t* found_inf,
-                                int flags, void* stream) {
+                                const sod_sgd_segment* segs, int nseg, const float* lr_dev, float inv_scale,
+                                const uint32_t* found_inf, int flags, void* stream) {
     using namespace sod;
     SOD_CHECK_ARG(param && mom && grad && n > 0, SOD_EINVAL);
     SOD_CHECK_ARG((n & 3) == 0 && aligned16(param) && aligned16(mom) && aligned16(grad), SOD_EALIGN);
@@ -321,8 +369,40 @@ extern "C" int sod_sgd_momentum(float* param, float* mom, float* grad, void* gra
     sgd_local_kernel<<<static_cast<unsigned>(blocks), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<float4*>(param), reinterpret_cast<float4*>(mom), reinterpret_cast<float4*>(grad),
         reinterpret_cast<uint2*>(grad16), reinterpret_cast<uint2*>(shadow16), nvec, t, inv_scale, found_inf,
-        (flags & SOD_SGD_ZERO_GRAD) ? 1 : 0);
+        (flags & SOD_SGD_ZERO_GRAD) ? 1 : 0, lr_dev);
     return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int sod_grad_gather16(const sod_gather_item* items, int nitems, void* dst16, int64_t dst_elems, void* stream) {
+    using namespace sod;
+    SOD_CHECK_ARG(nitems >= 0 && (nitems == 0 || items) && dst16 && dst_elems > 0, SOD_EINVAL);
+    SOD_CHECK_ARG(aligned16(dst16), SOD_EALIGN);
+    for (int base = 0; base < nitems; base += kGatherMax) {
+        GatherTable t;
+        t.n = (nitems - base < kGatherMax) ? nitems - base : kGatherMax;
+        unsigned chunks = 0;
+        for (int i = 0; i < t.n; ++i) {
+            const sod_gather_item& it = items[base + i];
+            if (it.src == nullptr || it.numel <= 0 || it.dst_offset < 0 || it.dst_offset + it.numel > dst_elems ||
+                it.numel > 0x7fffffffll)
+                return SOD_EINVAL;
+            if (it.dst_offset & 7) return SOD_EALIGN;
+            t.src[i] = it.src;
+            t.dst_off8[i] = static_cast<unsigned>(it.dst_offset >> 3);
+            t.numel[i] = static_cast<unsigned>(it.numel);
+            t.chunk0[i] = chunks;
+            chunks += static_cast<unsigned>((it.numel + kGatherChunk - 1) / kGatherChunk);
+        }
+        t.chunk0[t.n] = chunks;
+        if (chunks == 0) continue;
+        unsigned grid = chunks;
+        const unsigned cap = 8u * static_cast<unsigned>(dev_info().sm_count);
+        if (grid > cap) grid = cap;
+        grad_gather16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(t, reinterpret_cast<uint4*>(dst16));
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return static_cast<int>(e);
+    }
+    return SOD_OK;
 }
 
 extern "C" int sod_grad_nonfinite(const float* grad, int64_t n, uint32_t* found_inf, void* stream) {
@@ -350,7 +430,7 @@ extern "C" int sod_grad_merge_bf16(float* grad, void* grad16, int64_t n, void* s
 }
 
 extern "C" int sod_allreduce_sgd(const sod_comm* comm, uint64_t grad_off, uint64_t param_off, float* mom, void* shadow16,
-                                 int64_t n, const sod_sgd_segment* segs, int nseg, float inv_scale,
+                                 int64_t n, const sod_sgd_segment* segs, int nseg, const float* lr_dev, float inv_scale,
                                  const uint32_t* found_inf, int flags, void* stream) {
     using namespace sod;
     SOD_CHECK_ARG(comm && mom && n > 0, SOD_EINVAL);
@@ -374,10 +454,10 @@ extern "C" int sod_allreduce_sgd(const sod_comm* comm, uint64_t grad_off, uint64
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (mc)
         allreduce_sgd_kernel<true><<<grid, kThreads, 0, s>>>(c, grad_off, param_off, reinterpret_cast<float4*>(mom), nvec, t,
-                                                             scale, found_inf, zg, reinterpret_cast<uint2*>(shadow16));
+                                                             scale, found_inf, zg, reinterpret_cast<uint2*>(shadow16), lr_dev);
     else
         allreduce_sgd_kernel<false><<<grid, kThreads, 0, s>>>(c, grad_off, param_off, reinterpret_cast<float4*>(mom), nvec, t,
-                                                              scale, found_inf, zg, reinterpret_cast<uint2*>(shadow16));
+                                                              scale, found_inf, zg, reinterpret_cast<uint2*>(shadow16), lr_dev);
     return static_cast<int>(cudaGetLastError());
 }
 

@@ -183,13 +183,55 @@ __device__ __forceinline__ void publish(const CommDev& c, int use_mc, uint64_t s
         for (int q = 0; q < c.world; ++q) st_relaxed_sys_v2(reinterpret_cast<void*>(c.peer[q] + off), bits, tag);
     }
 }
+// slot of rank q's packet for `entry` in MY copy of the exchange area
+__device__ __forceinline__ const void* slot_of(const CommDev& c, uint64_t stats_off, int C, int q, int entry) {
+    return reinterpret_cast<const void*>(c.peer[c.rank] + stats_off + (static_cast<uint64_t>(q) * 2u * C + entry) * 8u);
+}
+// The W per-rank packets of one entry are requested TOGETHER (independent loads in flight: one L2 round trip instead
+// of W serialized ones — at world 8 that was ≈5 µs per launch); only packets whose tag has not arrived are polled.
+// Values are summed in rank order, so every rank obtains bit-identical statistics.
+__device__ __forceinline__ void collect_all(const CommDev& c, uint64_t stats_off, int C, int entry, uint32_t tag,
+                                            unsigned long long timeout, int& fail, float (&val)[SOD_MAX_WORLD]) {
+    uint2 v[SOD_MAX_WORLD];
+#pragma unroll
+    for (int q = 0; q < SOD_MAX_WORLD; ++q)
+        if (q < c.world) v[q] = ld_relaxed_sys_v2(slot_of(c, stats_off, C, q, entry));
+#pragma unroll
+    for (int q = 0; q < SOD_MAX_WORLD; ++q) {
+        val[q] = 0.f;
+        if (q < c.world)
+            val[q] = (v[q].y == tag) ? __uint_as_float(v[q].x) : wait_packet_sys(slot_of(c, stats_off, C, q, entry), tag, timeout, fail);
+    }
+}
+// two entries at once (forward: mean and M2 of one channel): all 2W packets are requested before any is examined
+__device__ __forceinline__ void collect_pair(const CommDev& c, uint64_t stats_off, int C, int e0, int e1, uint32_t tag,
+                                             unsigned long long timeout, int& fail, float (&v0)[SOD_MAX_WORLD],
+                                             float (&v1)[SOD_MAX_WORLD]) {
+    uint2 a[SOD_MAX_WORLD], b[SOD_MAX_WORLD];
+#pragma unroll
+    for (int q = 0; q < SOD_MAX_WORLD; ++q)
+        if (q < c.world) {
+            a[q] = ld_relaxed_sys_v2(slot_of(c, stats_off, C, q, e0));
+            b[q] = ld_relaxed_sys_v2(slot_of(c, stats_off, C, q, e1));
+        }
+#pragma unroll
+    for (int q = 0; q < SOD_MAX_WORLD; ++q) {
+        v0[q] = 0.f; v1[q] = 0.f;
+        if (q < c.world) {
+            v0[q] = (a[q].y == tag) ? __uint_as_float(a[q].x) : wait_packet_sys(slot_of(c, stats_off, C, q, e0), tag, timeout, fail);
+            v1[q] = (b[q].y == tag) ? __uint_as_float(b[q].x) : wait_packet_sys(slot_of(c, stats_off, C, q, e1), tag, timeout, fail);
+        }
+    }
+}
 __device__ __forceinline__ float collect(const CommDev& c, uint64_t stats_off, const uint2* ll_local, int C, int entry,
                                          uint32_t tag, unsigned long long timeout, int& fail) {
     if (c.world == 1) return wait_packet_gpu(ll_local + entry, tag, timeout, fail);
+    float val[SOD_MAX_WORLD];
+    collect_all(c, stats_off, C, entry, tag, timeout, fail, val);
     float acc = 0.f;
-    for (int q = 0; q < c.world; ++q)  // rank order: identical sum on every rank
-        acc += wait_packet_sys(reinterpret_cast<const void*>(c.peer[c.rank] + stats_off + (static_cast<uint64_t>(q) * 2u * C + entry) * 8u),
-                               tag, timeout, fail);
+#pragma unroll
+    for (int q = 0; q < SOD_MAX_WORLD; ++q)
+        if (q < c.world) acc += val[q];   // rank order: identical sum on every rank
     return acc;
 }
 
@@ -368,6 +410,113 @@ __device__ __forceinline__ void exchange(const BnGeom& g, const BnWork& w, const
     cbar();
 }
 
+// number of rows of strip t (all strips hold chunks_per_strip chunks except the last)
+__device__ __forceinline__ float strip_rows(const BnGeom& g, int t) {
+    const long long per = static_cast<long long>(g.chunks_per_strip) * g.chunk_rows;
+    const long long r0 = per * t;
+    const long long r1 = (r0 + per < g.rows) ? r0 + per : g.rows;
+    return static_cast<float>(r1 - r0);
+}
+
+// Forward statistics exchange in (mean, M2) form — the parallel-variance merge apex / torch SyncBN use
+// (torch/nn/modules/_functions.py: batch_norm_gather_stats_with_counts), evaluated in a fixed order.
+// On entry  red[j] = Σ (r − s) and red[C + j] = Σ (r − s)² over THIS strip, j = k*L + l (C = 8L channels), s = s_raw[channel].
+// On return red[j] = mean over all rows of all ranks, red[C + j] = biased variance, identical on every CTA and rank.
+__device__ __forceinline__ void exchange_moments(const BnGeom& g, const BnWork& w, const CommDev& c, int use_mc, uint64_t stats_off,
+                                                 uint32_t tag, float* red, const float* s_raw, int* s_fail) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int C = 8 * g.L;
+    const int n16 = 2 * C;
+    const int strips = static_cast<int>(gridDim.x);
+    const unsigned long long timeout = c.timeout_cycles ? c.timeout_cycles : 4000000000ull;
+    const float n_gpu = static_cast<float>(g.rows);
+    int fail = 0;
+    // hop 1a: my strip's (mean, M2) as packets — M2 = Σ(r−s)² − (Σ(r−s))²/n is well conditioned because s is a sample
+    uint2* mine = w.partials + static_cast<size_t>(blockIdx.x) * n16;
+    {
+        const float nb = strip_rows(g, blockIdx.x);
+        for (int j = tid; j < C; j += kThreads) {
+            const int ch = (j % g.L) * 8 + (j / g.L);
+            const float s1 = red[j], s2 = red[j + C];
+            st_packet_gpu(mine + j, s_raw[ch] + s1 / nb, tag);
+            st_packet_gpu(mine + C + j, fmaxf(s2 - s1 * (s1 / nb), 0.f), tag);
+        }
+    }
+    // hop 1b: my slice of CHANNELS; one warp per channel, lane t (+32u) holds strip t's pair
+    const int per = (C + strips - 1) / strips;
+    const int j0 = blockIdx.x * per;
+    const int j1 = (j0 + per < C) ? j0 + per : C;
+    for (int j = j0 + warp; j < j1; j += kWarps) {
+        constexpr int kMaxPer = (kMaxGrid + 31) / 32;
+        uint2 vm[kMaxPer], vq[kMaxPer];
+#pragma unroll
+        for (int u = 0; u < kMaxPer; ++u) {
+            const int t = lane + 32 * u;
+            if (t < strips) {
+                vm[u] = ld_packet_gpu(w.partials + static_cast<size_t>(t) * n16 + j);
+                vq[u] = ld_packet_gpu(w.partials + static_cast<size_t>(t) * n16 + C + j);
+            }
+        }
+        float m[kMaxPer], q2[kMaxPer], nt[kMaxPer];
+        float sm = 0.f;
+#pragma unroll
+        for (int u = 0; u < kMaxPer; ++u) {
+            const int t = lane + 32 * u;
+            m[u] = 0.f; q2[u] = 0.f; nt[u] = 0.f;
+            if (t < strips) {
+                m[u] = (vm[u].y == tag) ? __uint_as_float(vm[u].x) : wait_packet_gpu(w.partials + static_cast<size_t>(t) * n16 + j, tag, timeout, fail);
+                q2[u] = (vq[u].y == tag) ? __uint_as_float(vq[u].x) : wait_packet_gpu(w.partials + static_cast<size_t>(t) * n16 + C + j, tag, timeout, fail);
+                nt[u] = strip_rows(g, t);
+                sm = fmaf(nt[u], m[u], sm);
+            }
+        }
+        const float mean = warp_sum(sm) / n_gpu;
+        float sq = 0.f;
+#pragma unroll
+        for (int u = 0; u < kMaxPer; ++u) {
+            const float d = m[u] - mean;
+            sq += q2[u] + nt[u] * d * d;         // nt == 0 for the lanes without a strip
+        }
+        sq = warp_sum(sq);
+        if (lane == 0) {   // hop 2: this GPU's (mean, M2) to every rank
+            publish(c, use_mc, stats_off, w.ll_local, C, j, mean, tag);
+            publish(c, use_mc, stats_off, w.ll_local, C, C + j, sq, tag);
+        }
+    }
+    cbar();  // everyone has finished reading red[] (hop 1a) before it is overwritten
+    for (int j = tid; j < C; j += kThreads) {
+        float mean, var;
+        if (c.world == 1) {
+            const uint2 a = ld_packet_gpu(w.ll_local + j), b = ld_packet_gpu(w.ll_local + C + j);   // both in flight
+            mean = (a.y == tag) ? __uint_as_float(a.x) : wait_packet_gpu(w.ll_local + j, tag, timeout, fail);
+            var = ((b.y == tag) ? __uint_as_float(b.x) : wait_packet_gpu(w.ll_local + C + j, tag, timeout, fail)) / n_gpu;
+        } else {
+            float mq[SOD_MAX_WORLD], sq[SOD_MAX_WORLD];
+            collect_pair(c, stats_off, C, j, C + j, tag, timeout, fail, mq, sq);
+            float sm = 0.f;
+#pragma unroll
+            for (int q = 0; q < SOD_MAX_WORLD; ++q)
+                if (q < c.world) sm += mq[q];              // every rank contributes the same number of rows
+            mean = sm / static_cast<float>(c.world);
+            float acc = 0.f;
+#pragma unroll
+            for (int q = 0; q < SOD_MAX_WORLD; ++q)
+                if (q < c.world) {
+                    const float d = mq[q] - mean;
+                    acc += sq[q] + n_gpu * d * d;
+                }
+            var = acc / (n_gpu * static_cast<float>(c.world));
+        }
+        red[j] = mean;
+        red[C + j] = var;
+    }
+    if (fail) {
+        *s_fail = 1;
+        if (c.error_flag) atomicExch(c.error_flag, 0xDEAD0001u);
+    }
+    cbar();
+}
+
 __device__ __forceinline__ void ring_setup(Ring& ring, unsigned char* smem, const BnGeom& g, int nstream) {
     ring.full = reinterpret_cast<uint64_t*>(smem);
     ring.empty = ring.full + kMaxStages;
@@ -385,6 +534,9 @@ __device__ __forceinline__ void ring_setup(Ring& ring, unsigned char* smem, cons
         mbar_fence_init();
     }
     __syncthreads();  // all kBlock threads (the only block-wide barrier in the kernels)
+    // programmatic dependent launch: everything above overlapped the producing kernel's tail; nothing below may read
+    // global memory before that kernel has completed (a no-op for a normal launch)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // The load sequence of one CTA (training): chunks 0..n-1 for phase 1, then the chunks that did not stay resident,
@@ -445,11 +597,7 @@ __global__ void __launch_bounds__(kBlock, 1) syncbn_fwd_kernel(const __grid_cons
 
     // ---- consumers -------------------------------------------------------------------------------------
     const int l = tid % L;
-    const bool has_cb = prm.cbias1 != nullptr || prm.cbias2 != nullptr;
-    float cb[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-        cb[k] = ld_bias(prm.cbias1, prm.cbias_dtype, l * 8 + k) + ld_bias(prm.cbias2, prm.cbias_dtype, l * 8 + k);
+    float* s_raw = s_shift + kMaxC;      // per-channel shift of the statistics pass (first row of this strip)
     const T* __restrict__ gres = RES ? static_cast<const T*>(prm.res) : nullptr;
     T* __restrict__ gy = static_cast<T*>(prm.y);
     // affine / running parameters are fetched now so their DRAM latency hides behind phase 1
@@ -459,8 +607,11 @@ __global__ void __launch_bounds__(kBlock, 1) syncbn_fwd_kernel(const __grid_cons
     }
 
     if (training) {
-        // ---- phase 1: Σz, Σz² from shared memory ----------------------------------------------------------
-        float a[16];
+        // ---- phase 1: Σ(r − s), Σ(r − s)² from shared memory, r = x (+ pre) --------------------------------
+        // s = the strip's first row: sums of deviations from a sample of the distribution stay well conditioned where
+        // E[r²] − E[r]² loses the variance (|mean| ≫ std).  A folded conv bias is a per-channel constant: it moves the
+        // mean by b and nothing else, so it does not enter this pass at all.
+        float a[16], off[8];
 #pragma unroll
         for (int k = 0; k < 16; ++k) a[k] = 0.f;
         for (int i = 0; i < sp.n; ++i) {
@@ -469,6 +620,19 @@ __global__ void __launch_bounds__(kBlock, 1) syncbn_fwd_kernel(const __grid_cons
             const int npk = chunk_rows_of(g, sp.chunk0 + i) * L;
             const T* xs = reinterpret_cast<const T*>(ring.buf(s, 0));
             const T* ps = reinterpret_cast<const T*>(ring.buf(s, 1));
+            if (i == 0) {
+                IO<T>::load8(xs + l * 8, off);
+                if (has_pre) {
+                    float t[8];
+                    IO<T>::load8(ps + l * 8, t);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) off[k] += t[k];
+                }
+                if (tid < L) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) s_raw[l * 8 + k] = off[k];
+                }
+            }
             {
                 const int qb = tid;
                 typename IO<T>::Raw rx[PPT], rp[PPT];
@@ -492,14 +656,11 @@ __global__ void __launch_bounds__(kBlock, 1) syncbn_fwd_kernel(const __grid_cons
 #pragma unroll
                             for (int k = 0; k < 8; ++k) z[k] += t[k];
                         }
-                        if (has_cb) {
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) z[k] += cb[k];
-                        }
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
-                            a[k] += z[k];
-                            a[8 + k] = fmaf(z[k], z[k], a[8 + k]);
+                            const float d = z[k] - off[k];
+                            a[k] += d;
+                            a[8 + k] = fmaf(d, d, a[8 + k]);
                         }
                     }
                 }
@@ -508,18 +669,21 @@ __global__ void __launch_bounds__(kBlock, 1) syncbn_fwd_kernel(const __grid_cons
         }
         stamp(prm.w, 1);
         cta_reduce<16>(a, L, red);
-        exchange(g, prm.w, prm.c, prm.use_mc, prm.stats_off, call_tag(prm.tag, prm.epoch), red, &s_fail, 16, [](int, float) {});
+        exchange_moments(g, prm.w, prm.c, prm.use_mc, prm.stats_off, call_tag(prm.tag, prm.epoch), red, s_raw, &s_fail);
         stamp(prm.w, 2);
         // ---- per-channel coefficients --------------------------------------------------------------------
+        // The shift is built from the STORED mean (which includes the folded bias) in the same operation order the
+        // backward's mask-from-x variant uses (syncbn_bwd_kernel, "msc"/"msh"), so both derive the same sign for y.
         const float n = static_cast<float>(g.rows) * static_cast<float>(prm.c.world);
         for (int ch = tid; ch < C; ch += kThreads) {
             const int ll = ch >> 3, k = ch & 7;
-            const float mean = red[k * L + ll] / n;
-            const float var = fmaxf(red[(8 + k) * L + ll] / n - mean * mean, 0.f);
+            const float cbv = ld_bias(prm.cbias1, prm.cbias_dtype, ch) + ld_bias(prm.cbias2, prm.cbias_dtype, ch);
+            const float mean = red[k * L + ll] + cbv;
+            const float var = red[(8 + k) * L + ll];
             const float invstd = 1.0f / sqrtf(var + prm.eps);
             const float sc = invstd * s_scale[ch];
             s_scale[ch] = sc;
-            s_shift[ch] = s_shift[ch] - mean * sc;
+            s_shift[ch] = fmaf(cbv, sc, fmaf(-mean, sc, s_shift[ch]));
             if (blockIdx.x == 0) {
                 prm.smean[ch] = mean;
                 prm.sinvstd[ch] = invstd;
@@ -533,10 +697,11 @@ __global__ void __launch_bounds__(kBlock, 1) syncbn_fwd_kernel(const __grid_cons
         if (blockIdx.x == 0 && tid == 0 && prm.nbt) *prm.nbt += 1;
     } else {
         for (int ch = tid; ch < C; ch += kThreads) {
+            const float cbv = ld_bias(prm.cbias1, prm.cbias_dtype, ch) + ld_bias(prm.cbias2, prm.cbias_dtype, ch);
             const float invstd = 1.0f / sqrtf(prm.rvar[ch] + prm.eps);
             const float sc = invstd * s_scale[ch];
             s_scale[ch] = sc;
-            s_shift[ch] = s_shift[ch] - prm.rmean[ch] * sc;
+            s_shift[ch] = fmaf(cbv, sc, fmaf(-prm.rmean[ch], sc, s_shift[ch]));
         }
     }
     cbar();
@@ -546,7 +711,7 @@ __global__ void __launch_bounds__(kBlock, 1) syncbn_fwd_kernel(const __grid_cons
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         sc[k] = s_scale[l * 8 + k];
-        sh[k] = fmaf(cb[k], sc[k], s_shift[l * 8 + k]);     // (z + b)*sc + sh  ==  z*sc + (b*sc + sh)
+        sh[k] = s_shift[l * 8 + k];                          // the folded conv bias is already inside the shift
     }
     const bool relu = prm.relu != 0;
     const int nresident = training ? sp.n - nres0 : 0;
@@ -911,8 +1076,16 @@ static size_t bn_ws_layout(int C, BnWork* w, void* base) {
     return off;
 }
 
+// Every CTA spins on packets written by the other CTAs of the grid, so the whole grid has to be resident at once.
+// Geometry guarantees grid ≤ #SMs at one CTA per SM; what it cannot guarantee is that nothing else holds an SM.
+//   SOD_BN_LAUNCH_COOP : cooperative launch — the driver itself guarantees co-residency (or fails the launch) even
+//                        next to a concurrent kernel on another stream / under MPS / under a profiler replay;
+//   SOD_BN_LAUNCH_PDL  : programmatic dependent launch — the grid may be scheduled while the producing kernel drains;
+//                        the kernels execute griddepcontrol.wait before their first global read.
+// Independent of the mode, the launch is refused (SOD_EUNSUPPORTED) when the occupancy calculator says the kernel
+// cannot have one CTA per SM with the requested shared memory.
 template <typename K>
-static int launch_bn(K kern, const void* prm, const BnGeom& g, int nstream, cudaStream_t stream) {
+static int launch_bn(K kern, const void* prm, const BnGeom& g, int nstream, int flags, cudaStream_t stream) {
     const size_t smem = kSmemFixed + static_cast<size_t>(g.nstage) * nstream * g.chunk_bytes;
     static thread_local const void* configured[64] = {nullptr};   // per kernel instantiation, once per thread
     cudaError_t e;
@@ -921,11 +1094,34 @@ static int launch_bn(K kern, const void* prm, const BnGeom& g, int nstream, cuda
     if (!done) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_info().max_smem_optin - 1024);
         if (e != cudaSuccess) return static_cast<int>(e);
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, dev_info().max_smem_optin - 1024);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        if (per_sm < 1) return SOD_EUNSUPPORTED;
         for (auto& c : configured)
             if (c == nullptr) { c = reinterpret_cast<const void*>(kern); break; }
     }
+    if (g.strips > dev_info().sm_count) return SOD_EUNSUPPORTED;
     void* args[] = {const_cast<void*>(prm)};
-    e = cudaLaunchKernel(reinterpret_cast<const void*>(kern), dim3(g.strips), dim3(kBlock), args, smem, stream);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(g.strips);
+    cfg.blockDim = dim3(kBlock);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    unsigned na = 0;
+    if (flags & SOD_BN_LAUNCH_COOP) {
+        attr[na].id = cudaLaunchAttributeCooperative;
+        attr[na].val.cooperative = 1;
+        ++na;
+    } else if (flags & SOD_BN_LAUNCH_PDL) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    e = cudaLaunchKernelExC(&cfg, reinterpret_cast<const void*>(kern), args);
     return static_cast<int>(e);
 }
 
@@ -982,9 +1178,9 @@ extern "C" int sod_syncbn_fwd(const void* x, const void* pre_add, const void* re
     return SOD_DISPATCH_DTYPE(dtype, T, [&]() -> int {
         const bool r = residual != nullptr;
         switch (p.g.ppt) {
-            case 1: return r ? launch_bn(syncbn_fwd_kernel<T, 1, true>, &p, p.g, nstream, s) : launch_bn(syncbn_fwd_kernel<T, 1, false>, &p, p.g, nstream, s);
-            case 2: return r ? launch_bn(syncbn_fwd_kernel<T, 2, true>, &p, p.g, nstream, s) : launch_bn(syncbn_fwd_kernel<T, 2, false>, &p, p.g, nstream, s);
-            case 4: return r ? static_cast<int>(SOD_EUNSUPPORTED) : launch_bn(syncbn_fwd_kernel<T, 4, false>, &p, p.g, nstream, s);
+            case 1: return r ? launch_bn(syncbn_fwd_kernel<T, 1, true>, &p, p.g, nstream, flags, s) : launch_bn(syncbn_fwd_kernel<T, 1, false>, &p, p.g, nstream, flags, s);
+            case 2: return r ? launch_bn(syncbn_fwd_kernel<T, 2, true>, &p, p.g, nstream, flags, s) : launch_bn(syncbn_fwd_kernel<T, 2, false>, &p, p.g, nstream, flags, s);
+            case 4: return r ? static_cast<int>(SOD_EUNSUPPORTED) : launch_bn(syncbn_fwd_kernel<T, 4, false>, &p, p.g, nstream, flags, s);
             default: return static_cast<int>(SOD_EUNSUPPORTED);
         }
     });
@@ -1037,14 +1233,14 @@ extern "C" int sod_syncbn_bwd(const void* dy, const void* x, const void* pre_add
     return SOD_DISPATCH_DTYPE(dtype, T, [&]() -> int {
         if (flags & SOD_BN_L2_HINTS) {
             if (xmask)
-                return fold ? launch_bn(syncbn_bwd_kernel<T, 24, true, true>, &p, p.g, nstream, s)
-                            : launch_bn(syncbn_bwd_kernel<T, 16, true, true>, &p, p.g, nstream, s);
-            return fold ? launch_bn(syncbn_bwd_kernel<T, 24, false, true>, &p, p.g, nstream, s)
-                        : launch_bn(syncbn_bwd_kernel<T, 16, false, true>, &p, p.g, nstream, s);
+                return fold ? launch_bn(syncbn_bwd_kernel<T, 24, true, true>, &p, p.g, nstream, flags, s)
+                            : launch_bn(syncbn_bwd_kernel<T, 16, true, true>, &p, p.g, nstream, flags, s);
+            return fold ? launch_bn(syncbn_bwd_kernel<T, 24, false, true>, &p, p.g, nstream, flags, s)
+                        : launch_bn(syncbn_bwd_kernel<T, 16, false, true>, &p, p.g, nstream, flags, s);
         }
         if (xmask)
-            return fold ? launch_bn(syncbn_bwd_kernel<T, 24, true>, &p, p.g, nstream, s)
-                        : launch_bn(syncbn_bwd_kernel<T, 16, true>, &p, p.g, nstream, s);
-        return fold ? launch_bn(syncbn_bwd_kernel<T, 24>, &p, p.g, nstream, s) : launch_bn(syncbn_bwd_kernel<T, 16>, &p, p.g, nstream, s);
+            return fold ? launch_bn(syncbn_bwd_kernel<T, 24, true>, &p, p.g, nstream, flags, s)
+                        : launch_bn(syncbn_bwd_kernel<T, 16, true>, &p, p.g, nstream, flags, s);
+        return fold ? launch_bn(syncbn_bwd_kernel<T, 24>, &p, p.g, nstream, flags, s) : launch_bn(syncbn_bwd_kernel<T, 16>, &p, p.g, nstream, flags, s);
     });
 }

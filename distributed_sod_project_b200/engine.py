@@ -59,10 +59,13 @@ class Trainer:
         self.model.train()
         self._pinned_loss = torch.zeros(1, dtype=torch.float32).pin_memory()
         self._loss_event: torch.cuda.Event | None = None
-        # CUDA-graph replay of the whole iteration: one cudaGraphLaunch instead of ~1500 launches
-        self.use_graph = use_graph and not amp._cfg["dynamic"]
-        self._graph = None
-        self._graph_key = None
+        # CUDA-graph replay of the whole iteration: one cudaGraphLaunch instead of ~1500 launches.
+        # One graph per input shape (multi-scale training, reference utils/dataset.py:125-132, cycles through three);
+        # learning rates are read from a device table (FusedSGD.sync_lr), so the scheduler never forces a re-capture.
+        from .optim import FusedSGD
+        self.use_graph = use_graph and not amp._cfg["dynamic"] and isinstance(self.optimizer, FusedSGD)
+        self._graphs: dict = {}
+        self._cur = None
 
     @property
     def module(self):
@@ -70,6 +73,12 @@ class Trainer:
 
     def scheduler(self, total_num: int, lr_type: str = "poly", lr_decay: float = 0.9, warmup_epoch: int = 1):
         return CustomScheduler(self.optimizer, total_num, lr_type, dict(lr_decay=lr_decay, warmup_epoch=warmup_epoch))
+
+    def check_errors(self) -> None:
+        """raise if a device-side barrier / packet wait of either arena timed out (host sync: call it at log points)"""
+        for arena in (getattr(self.model, "arena", None), comm.small_arena() if self.world > 1 else None):
+            if arena is not None:
+                arena.check_error()
 
     # ----------------------------------------------------------------------------------------------
     def _iteration(self, x: torch.Tensor, m: torch.Tensor, report: bool):
@@ -93,9 +102,9 @@ class Trainer:
         reduced = comm.allreduce_tensor(loss.detach()) if self.world > 1 else loss.detach()   # train.py:306
         return reduced, items, preds
 
-    def _capture(self, x: torch.Tensor, m: torch.Tensor):
+    def _capture(self, x: torch.Tensor, m: torch.Tensor) -> dict:
         """warm up eagerly on a side stream, then record one whole iteration into a CUDA graph"""
-        self._static_x, self._static_m = x.clone(), m.clone()
+        static_x, static_m = x.clone(), m.clone()
         # the warm-up iterations (allocator, cuDNN autotune, autograd thread) must not move the training state
         flat = self.optimizer.flat
         snap = [flat.param.clone(), flat.mom.clone()] + [b.clone() for b in self.module.buffers()]
@@ -105,7 +114,7 @@ class Trainer:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(2):
-                self._iteration(self._static_x, self._static_m, report=False)
+                self._iteration(static_x, static_m, report=False)
         torch.cuda.current_stream().wait_stream(side)
         with torch.no_grad():
             flat.param.copy_(snap[0]); flat.mom.copy_(snap[1])
@@ -113,7 +122,6 @@ class Trainer:
                 b.copy_(old)
             if shadow_snap is not None:
                 flat.shadow16.copy_(shadow_snap)
-        self.optimizer.steps, self.optimizer._stepped = steps, stepped
         if self.world > 1:
             torch.distributed.barrier()
         torch.cuda.synchronize()
@@ -122,30 +130,39 @@ class Trainer:
         syncbn.begin_iteration(self.device, graph=True)
         try:
             with torch.cuda.graph(graph):
-                red, items, preds = self._iteration(self._static_x, self._static_m, report=False)
+                red, items, preds = self._iteration(static_x, static_m, report=False)
                 syncbn.end_iteration(self.device)
-                self._static_out = (red, items, preds)
         finally:
             syncbn.begin_iteration(self.device, graph=False)
-        self._graph = graph
-        self._graph_launches = _lib.launches - launches0      # hand-written kernels recorded in the graph
-        self._graph_key = (tuple(x.shape), tuple(m.shape), x.dtype, tuple(g["lr"] for g in self.optimizer.param_groups))
+        # capturing records, it does not execute: the optimizer has not stepped
+        self.optimizer.steps, self.optimizer._stepped = steps, stepped
+        return dict(graph=graph, x=static_x, m=static_m, out=(red, items, preds), launches=_lib.launches - launches0)
+
+    def _graph_for(self, x: torch.Tensor, m: torch.Tensor) -> dict:
+        key = (tuple(x.shape), tuple(m.shape), x.dtype)
+        ent = self._graphs.get(key)
+        if ent is None:                                       # first call with this input size
+            ent = self._graphs[key] = self._capture(x, m)
+        self._cur = ent
+        return ent
+
+    def _replay(self, ent: dict) -> None:
+        self.optimizer.sync_lr()                              # param_groups[i]["lr"] → device table, only when it moved
+        ent["graph"].replay()
+        self.optimizer.steps += 1
+        self.optimizer._stepped = True
+        _lib.count_launch(ent["launches"])
 
     def forward_backward_update(self, x: torch.Tensor, m: torch.Tensor, report: bool | None = None):
         """device tensors in, device loss out; no host synchronisation unless report strings are requested"""
         report = self.report_items if report is None else report
         if not self.use_graph:
             return self._iteration(x, m, report)
-        key = (tuple(x.shape), tuple(m.shape), x.dtype, tuple(g["lr"] for g in self.optimizer.param_groups))
-        if self._graph is None or key != self._graph_key:     # first call, new multi-scale size, or the lr moved
-            self._graph = None
-            self._capture(x, m)
-        self._static_x.copy_(x, non_blocking=True)
-        self._static_m.copy_(m, non_blocking=True)
-        self._graph.replay()
-        self.optimizer.steps += 1
-        _lib.count_launch(self._graph_launches)
-        red, items, preds = self._static_out
+        ent = self._graph_for(x, m)
+        ent["x"].copy_(x, non_blocking=True)
+        ent["m"].copy_(m, non_blocking=True)
+        self._replay(ent)
+        red, items, preds = ent["out"]
         if report:
             items = [f"{v:.5f}" for v in items[:2].tolist()]
         return red, items, preds
@@ -159,17 +176,17 @@ class Trainer:
     def step_from_host(self, x_pinned: torch.Tensor, m_pinned: torch.Tensor):
         """end-to-end form: pinned host batch → device (train.py:291-292) → iteration → loss back to pinned host
         memory.  The D2H read is asynchronous; `last_loss()` waits for it."""
-        if self.use_graph and self._graph is not None and tuple(x_pinned.shape) == self._graph_key[0]:
+        key = (tuple(x_pinned.shape), tuple(m_pinned.shape), x_pinned.dtype)
+        ent = self._graphs.get(key) if self.use_graph else None
+        if ent is not None:
             if PREFETCH_H2D:
-                self._stage_inputs(x_pinned, m_pinned)
+                self._stage_inputs(ent, x_pinned, m_pinned)
             else:
                 # H2D straight into the graph's static inputs
-                self._static_x.copy_(x_pinned, non_blocking=True)
-                self._static_m.copy_(m_pinned, non_blocking=True)
-            self._graph.replay()
-            self.optimizer.steps += 1
-            _lib.count_launch(self._graph_launches)
-            reduced = self._static_out[0]
+                ent["x"].copy_(x_pinned, non_blocking=True)
+                ent["m"].copy_(m_pinned, non_blocking=True)
+            self._replay(ent)
+            reduced = ent["out"][0]
         else:
             x = x_pinned.to(self.device, non_blocking=True)
             m = m_pinned.to(self.device, non_blocking=True)
@@ -178,33 +195,35 @@ class Trainer:
         self._loss_event = torch.cuda.Event()
         self._loss_event.record()
 
-    def _stage_inputs(self, x_pinned: torch.Tensor, m_pinned: torch.Tensor) -> None:
+    def _stage_inputs(self, ent: dict, x_pinned: torch.Tensor, m_pinned: torch.Tensor) -> None:
         """(PREFETCH_H2D, default on) the H2D copy of this call's batch runs on a copy
         stream into one of two staging buffers, so it overlaps the previous call's iteration (the host loop runs ahead:
         nothing in `step_from_host` blocks); the iteration's stream then only pays a device-to-device copy into the
         graph's static inputs.  Same contract as the plain path: every step's H2D and D2H stay inside the caller's
         timed region.  (The reference prefetches too: `BackgroundGenerator(tr_loader, max_prefetch=2)`, train.py:278-285.)"""
-        if getattr(self, "_copy_stream", None) is None or self._stage[0][0].shape != self._static_x.shape:
+        if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
-            self._stage = [(torch.empty_like(self._static_x), torch.empty_like(self._static_m)) for _ in range(2)]
-            self._stage_ready = [torch.cuda.Event(), torch.cuda.Event()]     # H2D into stage k has finished
-            self._stage_free = [None, None]                                  # the D2D out of stage k has finished
-            self._stage_idx = 0
-        k = self._stage_idx
-        self._stage_idx ^= 1
+        st = ent.get("stage")
+        if st is None:                                   # two staging buffers per captured input size
+            st = ent["stage"] = dict(buf=[(torch.empty_like(ent["x"]), torch.empty_like(ent["m"])) for _ in range(2)],
+                                     ready=[torch.cuda.Event(), torch.cuda.Event()],     # H2D into stage k has finished
+                                     free=[None, None],                                  # the D2D out of stage k has finished
+                                     idx=0)
+        k = st["idx"]
+        st["idx"] ^= 1
         cs, main = self._copy_stream, torch.cuda.current_stream()
-        if self._stage_free[k] is not None:
-            cs.wait_event(self._stage_free[k])
+        if st["free"][k] is not None:
+            cs.wait_event(st["free"][k])
         with torch.cuda.stream(cs):
-            self._stage[k][0].copy_(x_pinned, non_blocking=True)
-            self._stage[k][1].copy_(m_pinned, non_blocking=True)
-            self._stage_ready[k].record(cs)
-        main.wait_event(self._stage_ready[k])
-        self._static_x.copy_(self._stage[k][0])
-        self._static_m.copy_(self._stage[k][1])
+            st["buf"][k][0].copy_(x_pinned, non_blocking=True)
+            st["buf"][k][1].copy_(m_pinned, non_blocking=True)
+            st["ready"][k].record(cs)
+        main.wait_event(st["ready"][k])
+        ent["x"].copy_(st["buf"][k][0])
+        ent["m"].copy_(st["buf"][k][1])
         free = torch.cuda.Event()
         free.record(main)
-        self._stage_free[k] = free
+        st["free"][k] = free
 
     def last_loss(self) -> float:
         if self._loss_event is not None:

@@ -58,6 +58,10 @@ class FlatParams:
         self.param_off = self.grad_off = 0
         self.shadow16: torch.Tensor | None = None   # bf16 copy of `param`, refreshed by the fused step (amp O1 shadow)
         self.grad16: torch.Tensor | None = None     # bf16 gradients autograd accumulates for the shadowed tensors
+        # bf16 shadow leaves the convolutions consume (amp._install_shadow_weights): (leaf, element offset, steal)
+        # steal=True: `.grad` is left None so that autograd hands over cuDNN's gradient tensor as it is (no accumulate
+        # kernel per parameter); FusedSGD.step collects all of them into `grad16` with one sod_grad_gather16 launch
+        self.shadow_leaves: list[tuple[torch.Tensor, int, bool]] = []
         self._bind(copy_from_params=True)
 
     # -- mixed precision: bf16 shadow of the fp32 master ---------------------------------------------------
@@ -120,6 +124,23 @@ class FlatParams:
         raise KeyError("parameter not managed")
 
 
+def _same_physical_order(a: torch.Tensor, b: torch.Tensor) -> bool:
+    """both dense, and their elements laid out in memory in the same order — strides of size-1 dimensions carry no
+    information (a [K,C,1,1] weight is the same bytes channels-last or contiguous, but reports different strides)"""
+    if a.shape != b.shape:
+        return False
+    sa = [st for st, n in zip(a.stride(), a.shape) if n > 1]
+    sb = [st for st, n in zip(b.stride(), b.shape) if n > 1]
+    if sa != sb:
+        return False
+    need = 1
+    for st, n in sorted((st, n) for st, n in zip(a.stride(), a.shape) if n > 1):
+        if st != need:
+            return False
+        need *= n
+    return True
+
+
 class FusedSGD(Optimizer):
     """SGD with momentum / weight decay as one flat sm_100a kernel; gradient averaging folded in when
     distributed.  Arithmetic = torch.optim.SGD (torch/optim/sgd.py:343-380) with dampening 0, nesterov False."""
@@ -142,10 +163,29 @@ class FusedSGD(Optimizer):
         self._clean_version = self._grad_versions()
         self._stepped = False
         self.steps = 0
+        # learning rates as the kernels read them: a device table, rewritten (tiny fill kernels, by value) only when a
+        # param_group's lr has changed — so a captured iteration follows the scheduler without being re-captured
+        self._lr_dev = torch.zeros(_lib.SOD_MAX_SEGMENTS, dtype=torch.float32, device=self.flat.device) \
+            if self.flat.device.type == "cuda" else None
+        self._lr_sent: list[float | None] = [None] * _lib.SOD_MAX_SEGMENTS
 
     def _grad_versions(self):
         f = self.flat
-        return (f.grad._version, f.grad16._version if f.grad16 is not None else -1, id(f.grad))
+        return (f.grad._version, f.grad16._version if f.grad16 is not None else -1, id(f.grad), _lib.grad_writes)
+
+    def sync_lr(self) -> None:
+        """bring the device learning-rate table in line with `param_groups[i]["lr"]` (stream-ordered; a no-op while a
+        CUDA graph is being captured — the captured kernels read the table, whoever replays them calls this first)"""
+        if self._lr_dev is None or torch.cuda.is_current_stream_capturing():
+            return
+        n = 0
+        for g, (b, e) in zip(self.param_groups, self.flat.ranges):
+            if e > b:
+                lr = float(g["lr"])
+                if self._lr_sent[n] != lr:
+                    self._lr_dev[n].fill_(lr)
+                    self._lr_sent[n] = lr
+                n += 1
 
     # -- torch.optim.Optimizer protocol -------------------------------------------------------------------
     def zero_grad(self, set_to_none: bool = False):
@@ -162,6 +202,37 @@ class FusedSGD(Optimizer):
         for p, off in self.flat.slots:
             if p.grad is None or p.grad.data_ptr() != self.flat.grad.data_ptr() + 4 * off:
                 p.grad = FlatParams._view(self.flat.grad, off, p.data)
+        for leaf, off, steal in self.flat.shadow_leaves:
+            if steal:
+                leaf.grad = None
+            elif leaf.grad is None or leaf.grad.data_ptr() != self.flat.grad16.data_ptr() + 2 * off:
+                leaf.grad = FlatParams._view(self.flat.grad16, off, leaf)
+
+    def _gather_stolen(self) -> None:
+        """bf16 gradients autograd left in their own tensors (shadow leaves with steal=True, or any leaf whose `.grad`
+        was replaced) → flat `grad16`, one launch for all of them"""
+        f = self.flat
+        if not f.shadow_leaves:
+            return
+        base = f.grad16.data_ptr()
+        items = []
+        for leaf, off, _ in f.shadow_leaves:
+            g = leaf.grad
+            if g is None or g.data_ptr() == base + 2 * off:
+                continue
+            if g.dtype == f.grad16.dtype and g.is_cuda and g.numel() == leaf.numel() and _same_physical_order(g, leaf):
+                items.append((g.data_ptr(), off, g.numel()))
+            else:                                            # unusual layout / dtype: plain torch accumulate
+                FlatParams._view(f.grad16, off, leaf).add_(g.to(f.grad16.dtype))
+        if items:
+            key = tuple(items)
+            if getattr(self, "_gather_key", None) != key:    # eager steps see new addresses every time, graph capture once
+                self._gather_key = key
+                self._gather_arr = (_lib.sod_gather_item * len(items))(*[_lib.sod_gather_item(a, b, c) for a, b, c in items])
+            arr = self._gather_arr
+            rc = _lib.lib().sod_grad_gather16(arr, len(items), base, f.numel, _lib.stream_ptr())
+            _lib.check(rc, "sod_grad_gather16")
+            _lib.count_launch((len(items) + _lib.SOD_GATHER_MAX_ITEMS - 1) // _lib.SOD_GATHER_MAX_ITEMS)
 
     def _segments(self):
         segs = (_lib.sod_sgd_segment * (len(self.param_groups) + 1))()
@@ -184,12 +255,16 @@ class FusedSGD(Optimizer):
         if not f.param.is_cuda:
             raise _lib.SodError("FusedSGD.step needs CUDA parameters (no CPU fallback)")
         segs, n = self._segments()
+        self.sync_lr()
+        lr_dev = self._lr_dev.data_ptr()
+        self._gather_stolen()
         finf = self.found_inf.data_ptr() if self.found_inf is not None else None
         g16 = f.grad16.data_ptr() if f.grad16 is not None else None
         s16 = f.shadow16.data_ptr() if f.shadow16 is not None else None
         if f.arena is None:
             rc = _lib.lib().sod_sgd_momentum(f.param.data_ptr(), f.mom.data_ptr(), f.grad.data_ptr(), g16, s16, f.numel,
-                                             segs, n, float(self.inv_scale), finf, _lib.SOD_SGD_ZERO_GRAD, _lib.stream_ptr())
+                                             segs, n, lr_dev, float(self.inv_scale), finf, _lib.SOD_SGD_ZERO_GRAD,
+                                             _lib.stream_ptr())
             _lib.check(rc, "sod_sgd_momentum")
         else:
             a = f.arena
@@ -198,7 +273,7 @@ class FusedSGD(Optimizer):
                 _lib.check(rc, "sod_grad_merge_bf16")
                 _lib.count_launch()
             rc = _lib.lib().sod_allreduce_sgd(a.ref, f.grad_off, f.param_off, f.mom.data_ptr(), s16, f.numel, segs, n,
-                                              float(self.inv_scale), finf, _lib.SOD_SGD_ZERO_GRAD, _lib.stream_ptr())
+                                              lr_dev, float(self.inv_scale), finf, _lib.SOD_SGD_ZERO_GRAD, _lib.stream_ptr())
             _lib.check(rc, "sod_allreduce_sgd")
         _lib.count_launch()
         self._grads_clean = True
@@ -206,8 +281,31 @@ class FusedSGD(Optimizer):
         self._stepped = True
         self.steps += 1
 
+    def shard_bounds(self, rank: int, world: int) -> tuple[int, int]:
+        """element range of the flat buffers rank `rank` owns in `sod_allreduce_sgd` (csrc/sgd.cu: ceil(nvec/W) float4s)"""
+        nvec = self.flat.numel // 4
+        shard = (nvec + world - 1) // world
+        return min(rank * shard, nvec) * 4, min((rank + 1) * shard, nvec) * 4
+
+    @torch.no_grad()
+    def gather_momentum(self) -> None:
+        """world > 1: every rank only ever updates the momentum of the shard it owns (ZeRO-1 style); bring the full
+        buffer up to date on every rank.  COLLECTIVE (torch.distributed broadcasts, not on the hot path) — called by
+        `state_dict()`, so `state_dict()` must be entered by all ranks, like the reference's DDP/amp save path runs on
+        every process before rank 0 writes the file (utils/pipeline_ops.py:46-78)."""
+        f = self.flat
+        if f.arena is None:
+            return
+        import torch.distributed as dist
+        world = f.arena.world
+        for r in range(world):
+            lo, hi = self.shard_bounds(r, world)
+            if hi > lo:
+                dist.broadcast(f.mom[lo:hi], src=dist.get_global_rank(f.arena.group, r), group=f.arena.group)
+
     # momentum lives in the flat buffer; expose torch.optim.SGD's state layout on demand
     def state_dict(self):
+        self.gather_momentum()
         self.state.clear()
         if self._stepped:
             for g in self.param_groups:

@@ -74,6 +74,19 @@ class DistributedDataParallel(nn.Module):
         """Materialise the averaged gradients in place (what apex leaves in `.grad` after backward)."""
         if self.world == 1:
             return
+        # an optimizer that is not FusedSGD may have dropped the bound views (torch's zero_grad(set_to_none=True) is the
+        # default): autograd then produced fresh .grad tensors OUTSIDE the symmetric buffer.  Fold them in and rebind,
+        # so that what is averaged is what backward computed.
+        import torch
+        from .optim import FlatParams
+        with torch.no_grad():
+            for p, off in self.flat.slots:
+                view = FlatParams._view(self.flat.grad, off, p.data)
+                if p.grad is None:
+                    view.zero_()                      # no local gradient this time: contribute zeros, not last step's values
+                elif p.grad.data_ptr() != view.data_ptr():
+                    view.copy_(p.grad)
+                    p.grad = view
         self.arena.allreduce_(self.flat.grad_off, self.flat.numel, scale=1.0 / self.world, algo=2)
 
     def forward(self, *args, **kwargs):

@@ -23,6 +23,14 @@ from . import _lib, comm
 
 _state: dict = {}
 DEBUG_FLAGS = 0             # tools/bn_phases.py sets SOD_DEBUG_TIMING (4)
+# how the kernels are launched (csrc/syncbn.cu launch_bn): "plain", "coop" (cooperative launch: the driver guarantees
+# that the whole grid is co-resident, which the packet exchange relies on) or "pdl" (programmatic dependent launch)
+LAUNCH_MODE = os.environ.get("SOD_BN_LAUNCH", "plain")
+
+
+def _launch_flags() -> int:
+    return {"plain": 0, "coop": _lib.SOD_BN_LAUNCH_COOP, "pdl": _lib.SOD_BN_LAUNCH_PDL}[LAUNCH_MODE]
+
 FORCE_LOCAL = False         # bench.py roofline replay: run single-rank (no exchange) even inside a process group
 # BN+ReLU layers without a residual re-derive the ReLU mask from x in the backward instead of reading y (one input stream
 # less).  Default on since round 2: per-layer A/B on B200 (profiles/r02_call1_ab_bn_bwd.txt) 2531 → 2231 µs for the 84
@@ -111,7 +119,7 @@ class _SyncBNFn(torch.autograd.Function):
             mean.data_ptr(), invstd.data_ptr(), rows, c, float(momentum), float(eps), int(relu), int(training),
             cref, soff, seq, epoch, nbt.data_ptr() if nbt is not None else None,
             cb1.data_ptr() if cb1 is not None else None, cb2.data_ptr() if cb2 is not None else None, cb_dtype,
-            ws.data_ptr(), ws.numel(), DEBUG_FLAGS, _lib.stream_ptr())
+            ws.data_ptr(), ws.numel(), DEBUG_FLAGS | _launch_flags(), _lib.stream_ptr())
         _lib.check(rc, "sod_syncbn_fwd")
         _lib.count_launch()
         ctx.relu, ctx.has_pre, ctx.has_res = bool(relu), pre is not None, res is not None
@@ -158,11 +166,12 @@ def raw_backward(dy, x, pre, y, weight, mean, invstd, relu: bool, want_dres: boo
     dres = torch.empty_like(x) if want_dres else None
     if into is not None:
         dgamma, dbeta = into
-        flags = DEBUG_FLAGS | _lib.SOD_BN_ACCUMULATE_PARAM_GRADS
+        flags = DEBUG_FLAGS | _launch_flags() | _lib.SOD_BN_ACCUMULATE_PARAM_GRADS
+        _lib.grad_writes += 1          # bound .grad buffers change behind autograd's back (FusedSGD.zero_grad looks at this)
     else:
         dgamma = torch.empty(c, dtype=torch.float32, device=x.device)
         dbeta = torch.empty(c, dtype=torch.float32, device=x.device)
-        flags = DEBUG_FLAGS
+        flags = DEBUG_FLAGS | _launch_flags()
     if MASK_FROM_X and relu and not want_dres and bias is not None:
         flags |= _lib.SOD_BN_BWD_MASK_FROM_X
     if L2_HINTS:

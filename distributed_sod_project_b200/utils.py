@@ -44,11 +44,11 @@ class AvgMeter:
 
 
 def construct_print(out_str: str, total_length: int = 80) -> None:
-    """banner print of the reference (utils/misc.py:330-336)"""
-    s = str(out_str)
-    pad = max(total_length - len(s) - 4, 0)
-    left = pad // 2
-    print("=" * left + ">> " + s + " <<" + "=" * (pad - left))
+    """banner print with the reference's exact format (utils/misc.py:330-336): ` ===>> text <<=== `, the rule
+    shrinking with the text and collapsing to `==` once the text reaches `total_length`"""
+    text = str(out_str)
+    rule = "==" if len(text) >= total_length else "=" * ((total_length - len(text)) // 2 - 4)
+    print(f" {rule}>> {text} <<{rule} ")
 
 
 def check_mkdir(path: str) -> None:

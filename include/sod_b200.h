@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SOD_ABI_VERSION 5
+#define SOD_ABI_VERSION 6
 #define SOD_MAX_WORLD 8
 #define SOD_MAX_SEGMENTS 16
 #define SOD_COMM_MAX_BLOCKS 1024   /* flag rows per channel */
@@ -117,18 +117,33 @@ enum { SOD_SGD_ZERO_GRAD = 1, SOD_ALGO_NO_MULTIMEM = 2,
        SOD_DEBUG_TIMING = 4 /* syncbn: per-CTA globaltimer stamps behind the workspace (tools/bn_phases.py) */,
        SOD_BN_ACCUMULATE_PARAM_GRADS = 8 /* syncbn_bwd: dgamma/dbeta += (write straight into the bound .grad) */,
        SOD_ALGO_FORCE_MULTIMEM = 16 /* use NVLS even at world 2, where the default is peer loads */,
-       SOD_BN_BWD_MASK_FROM_X = 32 /* syncbn_bwd, EXPERIMENTAL (off by default in the host layer until it has been
-                                      measured on hardware): re-derive the ReLU mask from x with the forward's
-                                      arithmetic instead of reading y; needs relu, beta and dres == NULL */,
-       SOD_BN_L2_HINTS = 64 /* syncbn_bwd, EXPERIMENTAL (off by default, as above): L2 eviction-priority hints on the
-                               bulk copies — evict-last for chunks that are fetched twice, evict-first for last uses */ };
+       SOD_BN_BWD_MASK_FROM_X = 32 /* syncbn_bwd: re-derive the ReLU mask from x with the forward's arithmetic instead
+                                      of reading y (one input stream less); needs relu, beta and dres == NULL */,
+       SOD_BN_L2_HINTS = 64 /* syncbn_bwd: L2 eviction-priority hints on the bulk copies — evict-last for chunks that
+                               are fetched twice, evict-first for last uses */,
+       SOD_BN_LAUNCH_COOP = 128 /* syncbn_fwd/bwd: cooperative launch (driver-guaranteed co-residency of the grid) */,
+       SOD_BN_LAUNCH_PDL = 256 /* syncbn_fwd/bwd: programmatic dependent launch (prologue overlaps the producer's tail) */ };
 
+/* lr_dev (device, fp32[nseg], may be NULL): when given, the learning rate of segment i is read from lr_dev[i] at
+ * execution time instead of segs[i].lr — a captured CUDA graph then follows CustomScheduler
+ * (utils/pipeline_ops.py:225-229, stepped per epoch train.py:240-241 or per iteration train.py:288-289) with one
+ * small H2D copy per change and no re-capture. */
 int sod_sgd_momentum(float* param, float* mom, float* grad, void* grad16, void* shadow16, int64_t n,
-                     const sod_sgd_segment* segs, int nseg, float inv_scale, const uint32_t* found_inf, int flags,
-                     void* stream);
+                     const sod_sgd_segment* segs, int nseg, const float* lr_dev, float inv_scale,
+                     const uint32_t* found_inf, int flags, void* stream);
 int sod_allreduce_sgd(const sod_comm* comm, uint64_t grad_off, uint64_t param_off, float* mom, void* shadow16,
-                      int64_t n, const sod_sgd_segment* segs, int nseg, float inv_scale,
+                      int64_t n, const sod_sgd_segment* segs, int nseg, const float* lr_dev, float inv_scale,
                       const uint32_t* found_inf, int flags, void* stream);
+/* Multi-tensor gather of bf16 gradients into the flat bf16 gradient buffer (`grad16` above): item i copies
+ * numel elements from the dense tensor `src` to dst16[dst_offset ...] (dst_offset % 8 == 0).  Replaces the
+ * per-parameter accumulate kernels autograd launches at the end of backward (train.py:302): the weight gradients are
+ * left where cuDNN wrote them and collected by ONE launch (per SOD_GATHER_MAX_ITEMS tensors). */
+#define SOD_GATHER_MAX_ITEMS 160
+typedef struct {
+    const void* src;
+    int64_t dst_offset, numel;
+} sod_gather_item;
+int sod_grad_gather16(const sod_gather_item* items, int nitems, void* dst16, int64_t dst_elems, void* stream);
 /* grad[i] += float(grad16[i]); grad16[i] = 0   (world>1 pre-pass, one launch over the flat buffers) */
 int sod_grad_merge_bf16(float* grad, void* grad16, int64_t n, void* stream);
 /* *found_inf |= any(!isfinite(grad)) — the amp overflow check (train.py:299), one read of grad */
@@ -199,6 +214,30 @@ int sod_avgpool2x2_bwd(const void* dy, void* dx, int n, int h_out, int w_out, in
  * in (kh, kw) scan order, NaN propagates. */
 int sod_maxpool3x3s2_fwd(const void* x, void* y, void* argmax, int n, int h, int w, int c, int dtype, void* stream);
 int sod_maxpool3x3s2_bwd(const void* dy, const void* argmax, void* dx, int n, int h, int w, int c, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Data-side neighbours of the iteration.
+ *
+ * sod_preprocess_batch — the per-sample tensor transforms and the multi-scale collate of the reference's loader as one
+ * kernel over a uint8 batch: ToTensor + Normalize (utils/dataset.py:86-96), mask ToTensor (:110-116), optional
+ * left-right flip (utils/joint_transforms.py:19-23; flip_u8[i] != 0 mirrors sample i), and the collate's
+ * F.interpolate(img, bilinear, align_corners=False) / F.interpolate(mask, nearest) to (ho, wo)
+ * (utils/dataset.py:125-132).  img_u8 [n,hs,ws,3] HWC, mask_u8 [n,hs,ws] (may be NULL together with out_mask),
+ * out_img: storage [n,ho,wo,3] = a channels-last [n,3,ho,wo] tensor of out_dtype, out_mask fp32 [n,1,ho,wo].
+ *
+ * sod_saliency_* — sufficient statistics of the reference's evaluation metrics (utils/saliency_metric.py:8-239 as
+ * driven by train.py:383-412): quantize = ToPILImage's mul(255).byte() (optionally after a sigmoid); head = per image
+ * {min_u, max_u, max_gt, 0, n_fg, Σy, Σx, 0} (int64[8]); hist = per image uint32[4 quadrants][2 gt][256 k] joint
+ * histogram of k = u - min_u, quadrants split at split_yx[2i], split_yx[2i+1] (rows < y / cols < x first), counters
+ * ADDED to (zero them first).  Integer arithmetic only: results are exact and order independent.
+ * ------------------------------------------------------------------------------------------------ */
+int sod_preprocess_batch(const void* img_u8, const void* mask_u8, const void* flip_u8, void* out_img, int out_dtype,
+                         float* out_mask, int n, int hs, int ws, int ho, int wo, const float* mean3,
+                         const float* std3, void* stream);
+int sod_saliency_quantize(const void* pred, int dtype, void* out_u8, int64_t n, int apply_sigmoid, void* stream);
+int sod_saliency_head(const void* pred_u8, const void* gt_u8, int n, int h, int w, int64_t* head, void* stream);
+int sod_saliency_hist(const void* pred_u8, const void* gt_u8, int n, int h, int w, const int64_t* head,
+                      const int32_t* split_yx, uint32_t* hist, void* stream);
 
 #ifdef __cplusplus
 }

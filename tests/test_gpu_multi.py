@@ -91,7 +91,7 @@ def _w_allreduce_sgd(rank, world):
         mom = torch.tensor(ve, device="cuda")
         p.copy_(torch.tensor(pe)); g.copy_(torch.tensor(grads[rank]))
         torch.cuda.synchronize(); torch.distributed.barrier()
-        rc = _lib.lib().sod_allreduce_sgd(arena.ref, g_off, p_off, mom.data_ptr(), None, n, segs, 3, 0.5, None, flags,
+        rc = _lib.lib().sod_allreduce_sgd(arena.ref, g_off, p_off, mom.data_ptr(), None, n, segs, 3, None, 0.5, None, flags,
                                           torch.cuda.current_stream().cuda_stream)
         assert rc == 0
         torch.cuda.synchronize(); torch.distributed.barrier()
@@ -208,6 +208,8 @@ def _w_step(rank, world):
         assert np.isfinite(float(loss))
         if golden_ok:
             want = float(g[f"loss{it}"][rank])
+            # iterations 0 and 1: north_star's 1e-3.  Iteration 2: the reference's own float32 run is 3.9e-3 from its float64
+            # run at this configuration (profiles/r02_reference_fp32_vs_fp64.txt, "bs 8 size 128 iter 2"): 5e-3
             assert float(loss) == pytest.approx(want, rel=1e-3 if it < 2 else 5e-3), (rank, it, float(loss), want)
         if it == 0 and golden_ok:
             ref_l = g["logits0"][rank * bs:(rank + 1) * bs]
@@ -246,3 +248,122 @@ def _w_stress(rank, world):
 @needs2
 def test_skewed_ranks_stress():
     _spawn("_w_stress")
+
+
+def _w_checkpoint(rank, world, tmpdir):
+    """train 3 steps → save (collective: the momentum is sharded over the ranks) → step 4; a fresh process state resumed
+    from the file must produce the SAME step 4 bit for bit (reference utils/pipeline_ops.py:46-143; SURVEY §8e
+    'gather-on-save')."""
+    from distributed_sod_project_b200 import comm
+    from distributed_sod_project_b200.checkpoint import resume_checkpoint, save_checkpoint
+    from distributed_sod_project_b200.engine import Trainer
+    from distributed_sod_project_b200.synthetic import synth_batch
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.deterministic = True
+    torch.backends.cudnn.benchmark = False
+    full, state = os.path.join(tmpdir, "full.pth.tar"), os.path.join(tmpdir, "state.pth")
+
+    def batch(it):
+        x, m = synth_batch(1234 + rank + 1000 * it, 2, 64)
+        return x.cuda(), m.cuda()
+
+    tr = Trainer(model_name="res50", dtype=torch.float32, channels_last=True, report_items=False)
+    for it in range(3):
+        tr.forward_backward_update(*batch(it))
+    save_checkpoint(model=tr.model, optimizer=tr.optimizer, amp=None, exp_name="ckpt_test", current_epoch=1,
+                    full_net_path=full, state_net_path=state)
+    # what was written: full-length momentum with EVERY shard populated, compact storages
+    if rank == 0:
+        ck = torch.load(full, map_location="cpu", weights_only=False)
+        sd = ck["opti_state"]
+        bufs = [s["momentum_buffer"] for s in sd["state"].values()]
+        assert len(bufs) == sum(len(g["params"]) for g in sd["param_groups"])
+        big = [b for b in bufs if b.numel() > 10000]
+        assert all(float(b.abs().max()) > 0 for b in big)                  # no stale all-zero shard
+        assert all(b.untyped_storage().nbytes() == b.numel() * 4 for b in bufs)
+        assert os.path.getsize(full) < 2.3 * 4 * tr.optimizer.flat.numel     # ≈ params + momentum, not the whole arena
+    loss4, _, _ = tr.forward_backward_update(*batch(3))
+    want_p, want_loss = tr.optimizer.flat.param.clone(), float(loss4)
+    lo, hi = tr.optimizer.shard_bounds(rank, world)
+    want_v = tr.optimizer.flat.mom[lo:hi].clone()
+
+    tr2 = Trainer(model_name="res50", dtype=torch.float32, channels_last=True, report_items=False, seed=123)   # different init
+    epoch = resume_checkpoint(model=tr2.model, optimizer=tr2.optimizer, amp=None, exp_name="ckpt_test", load_path=full,
+                              mode="all", local_rank=rank)
+    assert epoch == 1
+    loss4b, _, _ = tr2.forward_backward_update(*batch(3))
+    assert float(loss4b) == want_loss
+    assert torch.equal(tr2.optimizer.flat.param, want_p)
+    assert torch.equal(tr2.optimizer.flat.mom[lo:hi], want_v)
+    tr.check_errors(); tr2.check_errors()
+
+
+@needs2
+def test_checkpoint_roundtrip_with_sharded_momentum(tmp_path):
+    _spawn("_w_checkpoint", args=(str(tmp_path),))
+
+
+def _w_adam(rank, world):
+    """an optimizer other than FusedSGD (make_optimizer('adam') → torch Adam, whose zero_grad drops the bound .grad
+    views): the wrapper must still average what backward computed."""
+    from distributed_sod_project_b200.parallel import DistributedDataParallel
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.Tanh(), torch.nn.Linear(32, 4)).cuda()
+    ddp = DistributedDataParallel(net, delay_allreduce=True)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-2)
+    for it in range(3):
+        g = torch.Generator().manual_seed(100 * it + rank)
+        x = torch.randn(8, 16, generator=g).cuda()
+        opt.zero_grad()                                   # set_to_none=True: autograd will allocate fresh gradients
+        twin = {k: v.detach().clone().requires_grad_(True) for k, v in net.named_parameters()}     # no hooks on these
+        local = torch.autograd.grad(torch.func.functional_call(net, twin, (x,)).pow(2).mean(), list(twin.values()))
+        want = []
+        for t in local:
+            t = t.clone(); torch.distributed.all_reduce(t); want.append(t / world)
+        ddp(x).pow(2).mean().backward()
+        torch.cuda.synchronize()
+        for p, w in zip(net.parameters(), want):
+            assert torch.allclose(p.grad, w, rtol=1e-5, atol=1e-7), it
+        opt.step()
+        ref = [p.detach().clone() for p in net.parameters()]
+        for r in ref:
+            torch.distributed.broadcast(r, 0)
+        assert all(torch.equal(a, b) for a, b in zip(ref, net.parameters()))
+    ddp.arena.check_error()
+
+
+@needs2
+def test_non_fused_optimizer_gets_averaged_gradients():
+    _spawn("_w_adam")
+
+
+def _w_graph_step(rank, world):
+    """the configuration the scaling bench runs: bf16, shadow weights, stolen weight gradients gathered by one launch,
+    whole iteration replayed as a CUDA graph with the learning rate moving underneath — against the eager run of the
+    same thing, and bit-identical parameters on all ranks throughout."""
+    from distributed_sod_project_b200.engine import Trainer
+    from distributed_sod_project_b200.synthetic import synth_batch
+    runs = {}
+    for use_graph in (False, True):
+        tr = Trainer(model_name="res50", dtype=torch.bfloat16, channels_last=True, report_items=False, use_graph=use_graph)
+        sched = tr.scheduler(total_num=5, lr_type="poly")
+        losses = []
+        for it in range(5):
+            sched.step(tr.optimizer, curr_epoch=it)
+            x, m = synth_batch(1234 + rank + 1000 * it, 4, 64 if it % 2 else 96)
+            red, _, _ = tr.forward_backward_update(x.cuda(), m.cuda())
+            losses.append(float(red))
+            flat = tr.optimizer.flat.param
+            other = flat.clone(); torch.distributed.broadcast(other, 0)
+            assert torch.equal(flat, other), (use_graph, it)
+        runs[use_graph] = (losses, tr.optimizer.flat.param.clone())
+        tr.check_errors()
+    assert runs[True][0] == pytest.approx(runs[False][0], rel=3e-3)
+    d = (runs[True][1] - runs[False][1]).abs().max() / runs[False][1].abs().max()
+    assert float(d) < 3e-3
+
+
+@needs2
+def test_graph_replay_world2_matches_eager():
+    _spawn("_w_graph_step")

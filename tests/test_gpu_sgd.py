@@ -16,9 +16,10 @@ def _segs(spec):
     return arr
 
 
-def _call(p, v, g, spec, inv_scale=1.0, found=None, flags=1):
+def _call(p, v, g, spec, inv_scale=1.0, found=None, flags=1, lr_dev=None):
     from distributed_sod_project_b200 import _lib
     rc = _lib.lib().sod_sgd_momentum(p.data_ptr(), v.data_ptr(), g.data_ptr(), None, None, p.numel(), _segs(spec), len(spec),
+                                     lr_dev.data_ptr() if lr_dev is not None else None,
                                      inv_scale, found.data_ptr() if found is not None else None, flags,
                                      torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
@@ -116,3 +117,61 @@ def test_fused_optimizer_follows_reference_trajectory(golden, kind):
     opt2.load_state_dict(sd)
     assert torch.equal(opt2.flat.mom, opt.flat.mom)
     assert "FusedSGD" in str(opt)
+
+
+def test_learning_rate_table_on_the_device_overrides_the_segment_values():
+    """ABI v6: with `lr_dev` the kernel reads each segment's learning rate from device memory at execution time — a
+    captured CUDA graph then follows CustomScheduler (reference utils/pipeline_ops.py:225-229) without re-capture."""
+    n = 8192
+    p0 = torch.linspace(-1, 1, n, device="cuda"); g0 = torch.full((n,), 0.5, device="cuda")
+    spec = [(0, n // 2, 123.0, 0.0, 0.0, 0), (n // 2, n, 456.0, 0.0, 0.0, 0)]     # by-value lrs must be ignored
+    lr = torch.tensor([0.1, 0.01] + [0.0] * 14, device="cuda")
+    p, v, g = p0.clone(), torch.zeros(n, device="cuda"), g0.clone()
+    graph = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        assert _call(p, v, g, spec, flags=0, lr_dev=lr) == 0        # warm-up launch
+        p.copy_(p0); v.zero_()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(graph, stream=s):
+            from distributed_sod_project_b200 import _lib
+            rc = _lib.lib().sod_sgd_momentum(p.data_ptr(), v.data_ptr(), g.data_ptr(), None, None, n, _segs(spec), 2, lr.data_ptr(),
+                                             1.0, None, 0, torch.cuda.current_stream().cuda_stream)
+            assert rc == 0
+    graph.replay(); torch.cuda.synchronize()
+    want = p0.clone(); want[:n // 2] -= 0.1 * 0.5; want[n // 2:] -= 0.01 * 0.5
+    assert torch.allclose(p, want, rtol=0, atol=1e-6)
+    lr[0].fill_(0.2); lr[1].fill_(0.0)                                # the scheduler moved: same graph, new rates
+    p.copy_(p0); v.zero_()
+    graph.replay(); torch.cuda.synchronize()
+    want = p0.clone(); want[:n // 2] -= 0.2 * 0.5
+    assert torch.allclose(p, want, rtol=0, atol=1e-6)
+
+
+def test_multi_tensor_gather_of_bf16_gradients():
+    """sod_grad_gather16: scattered dense bf16 tensors → their slots of the flat bf16 gradient buffer, bit-exact, incl.
+    sizes that are not multiples of 8, a misaligned source and more items than one launch carries."""
+    from distributed_sod_project_b200 import _lib
+    g = torch.Generator().manual_seed(3)
+    sizes = [1, 7, 8, 64, 4097, 8192, 8193, 147456, 2359296 + 3] + [33] * 170
+    flat_n = sum((s + 63) // 64 * 64 for s in sizes) + 64
+    flat = torch.full((flat_n,), -7.0, dtype=torch.bfloat16, device="cuda")
+    srcs, items, off = [], [], 64
+    for i, sz in enumerate(sizes):
+        t = torch.randn(sz + 1, generator=g).to(torch.bfloat16).cuda()
+        t = t[1:] if i % 5 == 4 else t[:sz]                  # every fifth source starts 2 bytes off a 16-byte boundary
+        srcs.append(t)
+        items.append(_lib.sod_gather_item(t.data_ptr(), off, sz))
+        off += (sz + 63) // 64 * 64
+    arr = (_lib.sod_gather_item * len(items))(*items)
+    rc = _lib.lib().sod_grad_gather16(arr, len(items), flat.data_ptr(), flat_n, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    off = 64
+    for t, sz in zip(srcs, sizes):
+        assert torch.equal(flat[off:off + sz], t), sz
+        pad = (sz + 63) // 64 * 64
+        assert bool((flat[off + sz:off + pad] == -7.0).all())           # nothing written outside the item
+        off += pad
+    bad = (_lib.sod_gather_item * 1)(_lib.sod_gather_item(srcs[0].data_ptr(), 4, 1))
+    assert _lib.lib().sod_grad_gather16(bad, 1, flat.data_ptr(), flat_n, torch.cuda.current_stream().cuda_stream) == -2

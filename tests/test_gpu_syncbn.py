@@ -221,3 +221,34 @@ def test_bwd_mask_from_x_agrees_with_mask_from_y(shape, dtype, with_pre, with_cb
     for a, b in zip(out[False][1:], out[True][1:]):
         if a is not None:
             torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-4 * rows ** 0.5 if dtype == torch.float32 else 2e-2 * rows ** 0.5)
+
+
+@pytest.mark.parametrize("mean,std", [(100.0, 0.1), (-50.0, 1e-2), (1000.0, 1.0), (0.0, 1.0)])
+@pytest.mark.parametrize("shape", [(16, 64, 80, 80), (4, 256, 20, 20), (16, 32, 160, 160), (2, 2048, 2, 2)])
+@pytest.mark.parametrize("with_bias", [False, True])
+def test_forward_statistics_survive_a_large_mean(mean, std, shape, with_bias):
+    """|mean| ≫ std (a post-residual channel): E[x²] − E[x]² in fp32 would lose the variance ((mean/std)² · 2⁻²⁴ is
+    6 % at 100/0.1 and > 100 % at 50/0.01).  The kernel accumulates deviations from a sample row and merges per-strip
+    (mean, M2) pairs — the scheme apex / torch SyncBN use — so the statistics must agree with the fp64 oracle.
+    Tolerances: invstd 2e-3 relative (limited by the fp32 input's own spacing at |x| ≈ |mean|), y 2e-2 absolute at the
+    two extreme settings (x·scale and the shift are ≈ |mean|/std ≈ 5·10³ and cancel in fp32: one ulp there is 5·10⁻⁴,
+    and the fp32 mean itself is only known to ulp(|mean|)/std)."""
+    n, c, h, w = shape
+    x = _mk(shape, torch.float32, 11, std, mean)
+    bn = _bn(c)
+    cb = (torch.linspace(-3, 3, c).cuda() * (1 + abs(mean))) if with_bias else None     # a huge folded conv bias changes nothing
+    y = bn.fused_forward(x, relu=False, conv_bias=(cb, None))
+    torch.cuda.synchronize()
+    x64 = x.detach().cpu().numpy().astype(np.float64)
+    if cb is not None:
+        x64 = x64 + cb.cpu().numpy().astype(np.float64)[None, :, None, None]
+    ref = obn.syncbn_forward([x64], bn.weight.detach().cpu().numpy().astype(np.float64),
+                             bn.bias.detach().cpu().numpy().astype(np.float64), np.zeros(c), np.ones(c), relu=False)
+    var_ref = 1.0 / ref["invstd"] ** 2
+    got_rv = (bn.running_var.double().cpu().numpy() - 0.9) / 0.1               # unbiased batch variance the kernel folded in
+    rows = n * h * w
+    np.testing.assert_allclose(got_rv * (rows - 1) / rows, var_ref - 1e-5, rtol=4e-3, atol=1e-7)
+    got_mean = bn.running_mean.double().cpu().numpy() / 0.1
+    np.testing.assert_allclose(got_mean, ref["mean"], rtol=1e-6, atol=1e-6 * max(1.0, abs(mean)))
+    extreme = abs(mean) / std > 500
+    np.testing.assert_allclose(y.double().cpu().numpy(), ref["ys"][0], rtol=0, atol=(4e-2 if with_bias else 2e-2) if extreme else 2e-3)

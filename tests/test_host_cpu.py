@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(h, name), f"{name} declared in include/sod_b200.h but not exported"
     assert declared == set(_lib.EXPORTS)
     lib = _lib.lib()
-    assert lib.sod_version() == 5
+    assert lib.sod_version() == 6
     assert lib.sod_comm_flag_bytes() == 4 * 1024 * 8 * 4
     assert lib.sod_syncbn_exchange_bytes(64) == 8 * 2 * 64 * 8
     assert b"workspace" in lib.sod_strerror(-3)
@@ -166,8 +166,14 @@ def test_shadow_weight_installation_is_structural_only():
     conv = m.sim8.h2h_1
     lo, hi = flat.shadow16.data_ptr(), flat.shadow16.data_ptr() + 2 * flat.numel
     assert lo <= conv._sod_w16.data_ptr() < hi and lo <= conv._sod_b16.data_ptr() < hi
-    assert conv._sod_w16.dtype == torch.bfloat16 and conv._sod_w16.requires_grad and conv._sod_w16.grad is not None
-    assert conv._sod_w16.grad.data_ptr() - flat.grad16.data_ptr() == conv._sod_w16.data_ptr() - flat.shadow16.data_ptr()
+    # weights: `.grad` stays None so that autograd hands over cuDNN's gradient tensor (gathered by the fused step);
+    # biases: bound to their slot of the flat bf16 gradient buffer (the SyncBN backward adds into it)
+    assert conv._sod_w16.dtype == torch.bfloat16 and conv._sod_w16.requires_grad and conv._sod_w16.grad is None
+    assert conv._sod_b16.grad.data_ptr() - flat.grad16.data_ptr() == conv._sod_b16.data_ptr() - flat.shadow16.data_ptr()
+    leaves = {id(t): (off, steal) for t, off, steal in flat.shadow_leaves}
+    assert leaves[id(conv._sod_w16)] == (flat.offset_of(conv.weight), True)
+    assert leaves[id(conv._sod_b16)] == (flat.offset_of(conv.bias), False)
+    assert len(leaves) == 105 + 46
     assert torch.equal(conv._sod_w16.detach().float(), conv.weight.detach().to(torch.bfloat16).float())
     frozen = m.div_2[0]
     assert frozen._sod_w16.requires_grad                       # div_2 still receives gradients (it is only left un-optimised)

@@ -81,6 +81,11 @@ def main_worker(local_rank, ngpus_per_node, world_size, args, exp_name, path_con
         init_process(args.ip, args.port, local_rank, world_size)
     batch_size_single_gpu = cfg["batch_size"] // ngpus_per_node                        # reference train.py:119
 
+    if not cfg.get("synthetic", True):
+        # decoding real datasets (reference utils/dataset.py:72-116, PIL + torchvision workers) is outside the hot path this
+        # repository covers: refuse loudly rather than silently train on noise
+        raise NotImplementedError('user_config["synthetic"] is False, but only the synthetic loader is wired into this train.py; '
+                                  "feed real batches through distributed_sod_project_b200.pipeline.preprocess_batch instead")
     loader = SyntheticLoader(batch_size_single_gpu, cfg.get("synthetic_iters_per_epoch", 20), cfg["input_size"],
                              cfg["size_list"], local_rank)
     total_iter_num = cfg["epoch_num"] * len(loader)
@@ -92,9 +97,9 @@ def main_worker(local_rank, ngpus_per_node, world_size, args, exp_name, path_con
     trainer = Trainer(model_name=cfg["model"], lr=cfg["lr"], momentum=cfg["momentum"], weight_decay=cfg["weight_decay"],
                       nesterov=cfg["nesterov"], optim=cfg["optim"], reduction=cfg["reduction"], use_aux_loss=cfg["use_aux_loss"],
                       dtype=dtype, channels_last=cfg.get("channels_last", True), report_items=True,
-                      # a captured iteration bakes its shapes and learning rates: multi-scale batches and a per-iteration
-                      # schedule (`sche_usebatch`) would re-capture every step, so they run eagerly
-                      use_graph=cfg.get("cuda_graph", False) and cfg["size_list"] is None and not cfg["sche_usebatch"])
+                      # one captured graph per input size; learning rates are read from a device table, so multi-scale
+                      # batches and a per-iteration schedule (`sche_usebatch`) replay graphs too
+                      use_graph=cfg.get("cuda_graph", False))
     scheduler = trainer.scheduler(total_iter_num if cfg["sche_usebatch"] else cfg["epoch_num"], cfg["lr_type"], cfg["lr_decay"],
                                   cfg["warmup_epoch"])
     if local_rank == 0:
@@ -115,6 +120,7 @@ def main_worker(local_rank, ngpus_per_node, world_size, args, exp_name, path_con
             scheduler.step(optimizer=trainer.optimizer, curr_epoch=curr_epoch)
         trainer.model.train()
         record = AvgMeter()
+        loss_acc, seen = torch.zeros((), device="cuda"), 0      # Σ loss·n of this epoch accumulated on the device, Σ n on the host
         t0 = time.time()
         for batch_id, (inputs, masks, names) in enumerate(loader):
             curr_iter = curr_epoch * len(loader) + batch_id
@@ -124,27 +130,32 @@ def main_worker(local_rank, ngpus_per_node, world_size, args, exp_name, path_con
             masks = masks.cuda(non_blocking=True)
             want_log = local_rank == 0 and cfg["print_freq"] > 0 and (curr_iter + 1) % cfg["print_freq"] == 0
             reduced, items, _ = trainer.forward_backward_update(inputs, masks, report=want_log)
+            # reference train.py:311 updates the running average every iteration; here that costs no host sync
+            loss_acc.add_(reduced.detach().reshape(()), alpha=float(inputs.size(0)))
+            seen += inputs.size(0)
             if want_log:                                                                 # host sync only when printing
                 loss_val = float(reduced.item())
-                record.update(loss_val, inputs.size(0))
+                record.val, record.sum, record.count = loss_val, float(loss_acc.item()), seen
+                record.avg = record.sum / max(seen, 1)
+                trainer.check_errors()                                                   # device-side barrier / packet timeouts
                 lr_str = ",".join(f"{g['lr']:.7f}" for g in trainer.optimizer.param_groups)
                 log = (f"[I:{batch_id}/{len(loader)}/{curr_iter}/{total_iter_num}][E:{curr_epoch}:{cfg['epoch_num']}]>[{exp_name}]"
                        f"[Lr:{lr_str}][Avg:{record.avg:.5f}|Cur:{loss_val:.5f}|{items}]")
                 print(log)
                 write_data_to_file(log, path_config["tr_log"])
         torch.cuda.synchronize()
+        trainer.check_errors()
         if local_rank == 0:
             n_img = len(loader) * batch_size_single_gpu * max(world_size, 1)
             construct_print(f"epoch {curr_epoch}: {time.time() - t0:.2f}s, {n_img / (time.time() - t0):.1f} img/s")
-            if (cfg["save_freq"] > 0 and (curr_epoch + 1) % cfg["save_freq"] == 0) or curr_epoch == cfg["epoch_num"] - 1:
-                save_checkpoint(model=trainer.model, optimizer=trainer.optimizer, amp=amp if cfg["use_amp"] else None,
-                                exp_name=exp_name, current_epoch=curr_epoch + 1, full_net_path=path_config["final_full_net"],
-                                state_net_path=path_config["final_state_net"])          # utils/pipeline_ops.py:46-78 layout
+        if (cfg["save_freq"] > 0 and (curr_epoch + 1) % cfg["save_freq"] == 0) or curr_epoch == cfg["epoch_num"] - 1:
+            # every rank enters (the sharded momentum is gathered collectively), rank 0 writes, all leave through a barrier
+            save_checkpoint(model=trainer.model, optimizer=trainer.optimizer, amp=amp if cfg["use_amp"] else None,
+                            exp_name=exp_name, current_epoch=curr_epoch + 1, full_net_path=path_config["final_full_net"],
+                            state_net_path=path_config["final_state_net"], write=local_rank == 0)   # utils/pipeline_ops.py:46-78
     construct_print("End Training...")
+    trainer.check_errors()
     if dist.is_initialized():
-        arena = getattr(trainer.model, "arena", None)
-        if arena is not None:
-            arena.check_error()
         dist.destroy_process_group()
 
 
