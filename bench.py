@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--multiscale", action="store_true",
                     help="BASELINE config 4: one size of {256,320,384} per batch (rank-shared RNG), as the reference's multi-scale collate")
     ap.add_argument("--no-parity-check", action="store_true", help="skip the untimed world>1 parity leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the ride-along measurements (multi-scale, sweep, stock-torch arm)")
     return ap.parse_args()
 
 
@@ -414,6 +415,103 @@ def parity_check(tr, rank: int, world: int) -> dict:
     return out
 
 
+# ----------------------------------------------------------------------------------------------------
+# ride-along measurements (BASELINE configs 4 and 5, SyncBN exchange cost, same-box stock-torch comparator)
+# ----------------------------------------------------------------------------------------------------
+def extra_multiscale(tr, rank, world, timed, steps=12):
+    """BASELINE config 4: multi-scale {256,320,384}, one size per batch (rank-shared RNG), on the trainer that was just
+    timed — two more graphs are captured (the 320 one exists), then `steps` iterations are timed like the headline."""
+    import random as _random
+    from distributed_sod_project_b200.synthetic import synth_batch
+    sizes = (256, 320, 384)
+    dev = {}
+    for k, sz in enumerate(sizes):
+        dev[sz] = [tuple(t.cuda() for t in synth_batch(4321 + rank + 100 * i + k, BS, sz)) for i in range(2)]
+    for sz in sizes:                                    # warm-up: capture the missing graphs, run each size twice
+        for i in range(2):
+            tr.forward_backward_update(*dev[sz][i])
+    rng = _random.Random(7)
+    order = [sizes[rng.randrange(3)] for _ in range(steps)]
+    ms = timed(lambda i: tr.forward_backward_update(*dev[order[i]][i % 2]), steps)
+    tr.check_errors()
+    return {"value": world * BS * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps, "sizes": list(sizes),
+            "order": order, "graphs": len(getattr(tr, "_graphs", {})),
+            "note": "one captured graph per size, learning rates from the device table; same timing discipline as the headline"}
+
+
+def extra_sweep(world, timed):
+    """BASELINE config 5 (short form; `--sweep` is the long one): peer-memory all-reduce vs torch NCCL, fp32, in place"""
+    if world < 2:
+        return None
+    from distributed_sod_project_b200 import comm
+    sizes = [64 << 10, 1 << 20, 16 << 20, 99_625_220 // 16 * 16]
+    arena = comm.Arena(payload_bytes=sizes[-1] + 4096)
+    off = arena.alloc(sizes[-1])
+    rows = []
+    for nbytes in sizes:
+        n = nbytes // 4
+        ref = torch.zeros(n, device="cuda")
+        arena.view(off, n, torch.float32).zero_()
+        row = {"bytes": nbytes}
+        for name, fn in (("nccl", lambda: dist.all_reduce(ref)), ("sod", lambda: arena.allreduce_(off, n, algo=0))):
+            for _ in range(3):
+                fn()
+            iters = 20 if nbytes <= (16 << 20) else 8
+            us = timed(lambda i: fn(), iters) / iters * 1e3
+            row[name] = {"us": us, "bus_gbs": 2 * (world - 1) / world * nbytes / (us * 1e-6) / 1e9}
+        row["frac_of_nvlink_900"] = row["sod"]["bus_gbs"] / 900.0
+        rows.append(row)
+    arena.check_error()
+    return {"world": world, "multicast": arena.has_multicast, "rows": rows}
+
+
+def extra_syncbn_exchange(world, timed, dtype):
+    """what one SyncBN statistics exchange costs across ranks: the same layer through the same kernel with and without
+    the cross-rank hop (FORCE_LOCAL), next to an NCCL all-reduce of the 2C-float payload the reference's SyncBN sends"""
+    if world < 2:
+        return None
+    from distributed_sod_project_b200 import syncbn as _sbn
+    from distributed_sod_project_b200.syncbn import SyncBatchNorm
+    out = {}
+    for (n, c, h, w) in ((16, 256, 20, 20), (16, 64, 80, 80)):
+        x = torch.randn((n, c, h, w), device="cuda", dtype=dtype).contiguous(memory_format=torch.channels_last)
+        bn = SyncBatchNorm(c).cuda()
+        res = {}
+        with torch.no_grad():
+            for tag, local_only in (("world", False), ("local", True)):
+                _sbn.FORCE_LOCAL = local_only
+                try:
+                    for _ in range(5):
+                        bn.fused_forward(x, relu=True)
+                    res[tag] = timed(lambda i: bn.fused_forward(x, relu=True), 50) / 50 * 1e3
+                finally:
+                    _sbn.FORCE_LOCAL = False
+        payload = torch.zeros(2 * c, device="cuda")
+        for _ in range(5):
+            dist.all_reduce(payload)
+        nccl = timed(lambda i: dist.all_reduce(payload), 50) / 50 * 1e3
+        extra_us = max(res["world"] - res["local"], 1e-3)
+        out[f"{n}x{c}x{h}x{w}"] = {"fwd_us_world": res["world"], "fwd_us_local": res["local"], "exchange_us": extra_us,
+                                   "nccl_allreduce_2C_us": nccl, "payload_bytes": 8 * c,
+                                   "bus_gbs": 2 * (world - 1) / world * 8 * c / (extra_us * 1e-6) / 1e9}
+    return out
+
+
+def extra_torch_arm(args, dtype, rank, world, timed, steps=8):
+    """the same iteration with stock PyTorch on the same GPUs (world > 1: nn.SyncBatchNorm + DistributedDataParallel over
+    NCCL) — the comparator SURVEY §2 names, measured in the same process right after the headline"""
+    from distributed_sod_project_b200.synthetic import synth_batch
+    tt = TorchEagerTrainer(args.model, dtype)
+    batches = [tuple(t.cuda() for t in synth_batch(1234 + rank + 100 * i, BS, SIZE)) for i in range(2)]
+    for i in range(3):
+        tt.forward_backward_update(*batches[i % 2])
+    ms = timed(lambda i: tt.forward_backward_update(*batches[i % 2]), steps)
+    del tt
+    torch.cuda.empty_cache()
+    return {"value": world * BS * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
+            "what": "nn.BatchNorm2d" if world == 1 else "nn.SyncBatchNorm + DistributedDataParallel (NCCL)"}
+
+
 def run_b200_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -561,6 +659,20 @@ def run_b200_arm(args):
                                    "frac_of_hbm": gbs / peaks()[0]["hbm_gbs"]}
     except Exception as ex:                              # noqa: BLE001
         extras["step_error"] = repr(ex)
+    if not args.multiscale and not args.no_extras:
+        # BASELINE configs 4 and 5 and the same-box comparator ride along with every default run, so that the round-end
+        # 1/2/4/8-GPU runs record them too (every rank takes part; a failure here never costs the headline line)
+        for name, fn in (("multiscale", lambda: extra_multiscale(tr, rank, world, timed)),
+                         ("allreduce_sweep", lambda: extra_sweep(world, timed)),
+                         ("syncbn_exchange", lambda: extra_syncbn_exchange(world, timed, dtype)),
+                         ("torch_same_box", lambda: extra_torch_arm(args, dtype, rank, world, timed))):
+            try:
+                res = fn()
+                if res is not None:
+                    extras[name] = res
+            except Exception as ex:                      # noqa: BLE001
+                extras[name] = {"error": repr(ex)}
+            log(f"extra {name} done")
 
     if rank != 0:
         if world > 1:
@@ -577,9 +689,13 @@ def run_b200_arm(args):
     roof = {"bound": "hbm", "kernel": "syncbn_bwd_kernel (84 launches/iteration, replayed alone on the model's layer shapes, "
                                       "L2 flushed between launches)",
             "achieved": bw, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": bw / pk["hbm_gbs"], "peak_kind": pk_kind,
-            "traffic": None, "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": avg_bytes,
-            "traffic_note": "per-launch DRAM traffic is only available from ncu for single layers: [16,64,160,160] bf16 backward moves "
-                            "244.8 MB read + 29.7 MB written in-kernel against 209.7 MB algorithmic (profiles/r01_syncbn_full_raw.csv)"}
+            "traffic": None, "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": avg_bytes}
+    try:        # dram__bytes_read + dram__bytes_write per launch, from the committed ncu pass over the same 84 launches (tools/bn_dram.py)
+        dram = json.load(open(os.path.join(ROOT, "profiles", "r02_syncbn_bwd_dram.json")))
+        roof["traffic"] = dram["avg_dram_bytes_per_launch"]
+        roof["traffic_source"] = "profiles/r02_syncbn_bwd_dram.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, each launch cold)"
+    except (OSError, KeyError, ValueError):
+        roof["traffic_source"] = "no committed ncu capture for this kernel revision"
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",

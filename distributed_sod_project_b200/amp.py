@@ -59,6 +59,11 @@ def _install_shadow_weights(model, flat) -> int:
 
         def forward(x, m=m):
             if torch.is_autocast_enabled() and x.is_cuda:
+                if m._sod_b16 is not None and m.padding_mode == "zeros" and x.dtype == m._sod_w16.dtype:
+                    from . import resample
+                    y = resample.conv_bias(m, x, m._sod_w16, m._sod_b16)     # bias gradient by sod_colsum
+                    if y is not None:
+                        return y
                 return m._conv_forward(x, m._sod_w16, m._sod_b16)
             return m._conv_forward(x, m.weight, m.bias)         # eval / fp32 use: the master copy
 

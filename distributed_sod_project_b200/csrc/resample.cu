@@ -223,3 +223,83 @@ extern "C" int sod_avgpool2x2_bwd(const void* dy, void* dx, int n, int h_out, in
         return static_cast<int>(cudaGetLastError());
     });
 }
+
+// ------------------------------------------------------------------------------------------------
+// column sum of a channels-last matrix [rows, C] — the bias gradient of a convolution that does NOT feed a
+// BatchNorm (the five `trans*` 1x1 convolutions, network/TestModel.py:32-36; their bias gradient is Σ_rows dy).
+// Deterministic: per-CTA partials in a workspace, the LAST CTA to finish (ticket counter) adds them in CTA order.
+// ------------------------------------------------------------------------------------------------
+namespace sod {
+namespace {
+
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, T* __restrict__ out, long long rows, int L,
+                                                      float* __restrict__ partial, unsigned* __restrict__ ticket) {
+    __shared__ float s_acc[256 * 8];
+    __shared__ bool s_last;
+    const int tid = threadIdx.x;
+    const int l = tid % L, r0 = tid / L, R = 256 / L;       // L ≤ 256 lanes (8 channels each), R rows per pass
+    const int C = L * 8;
+    float a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = 0.f;
+    if (r0 < R) {
+        for (long long r = static_cast<long long>(blockIdx.x) * R + r0; r < rows; r += static_cast<long long>(gridDim.x) * R) {
+            float v[8];
+            IO<T>::load8(x + r * C + l * 8, v);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] += v[k];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s_acc[tid * 8 + k] = a[k];
+    __syncthreads();
+    float* mine = partial + static_cast<size_t>(blockIdx.x) * C;
+    for (int ch = tid; ch < C; ch += 256) {
+        const int ll = ch >> 3, k = ch & 7;
+        float t = 0.f;
+        for (int rr = 0; rr < R; ++rr) t += s_acc[(rr * L + ll) * 8 + k];
+        mine[ch] = t;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int ch = tid; ch < C; ch += 256) {
+        float t = 0.f;
+        for (unsigned b = 0; b < gridDim.x; ++b) t += __ldcg(partial + static_cast<size_t>(b) * C + ch);
+        IO<T>::store1(out + ch, t);
+    }
+    if (tid == 0) *ticket = 0;                               // ready for the next launch on this stream
+}
+
+}  // namespace
+}  // namespace sod
+
+extern "C" size_t sod_colsum_workspace_bytes(void) { return static_cast<size_t>(296) * 2048 * sizeof(float) + 256; }
+
+extern "C" int sod_colsum(const void* x, void* out, int64_t rows, int c, int dtype, void* workspace, size_t workspace_bytes,
+                          void* stream) {
+    using namespace sod;
+    SOD_CHECK_ARG(x && out && workspace && rows > 0 && c > 0, SOD_EINVAL);
+    SOD_CHECK_ARG((c % 8) == 0 && c <= 2048, SOD_EUNSUPPORTED);
+    const int L = c / 8;
+    SOD_CHECK_ARG((L & (L - 1)) == 0, SOD_EUNSUPPORTED);
+    SOD_CHECK_ARG(aligned16(x) && aligned16(workspace), SOD_EALIGN);
+    SOD_CHECK_ARG(workspace_bytes >= sod_colsum_workspace_bytes(), SOD_EWORKSPACE);
+    const int R = 256 / L;
+    long long grid = (rows + static_cast<long long>(R) * 8 - 1) / (static_cast<long long>(R) * 8);   // ≥ 8 passes per CTA
+    const long long cap = 2ll * dev_info().sm_count;
+    if (grid > cap) grid = cap;
+    if (grid > 296) grid = 296;
+    if (grid < 1) grid = 1;
+    unsigned* ticket = reinterpret_cast<unsigned*>(workspace);               // first 256 bytes: ticket (zeroed once by the host)
+    float* partial = reinterpret_cast<float*>(static_cast<char*>(workspace) + 256);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    return SOD_DISPATCH_DTYPE(dtype, T, [&]() -> int {
+        colsum_kernel<T><<<static_cast<unsigned>(grid), 256, 0, s>>>(static_cast<const T*>(x), static_cast<T*>(out), rows, L, partial, ticket);
+        return static_cast<int>(cudaGetLastError());
+    });
+}

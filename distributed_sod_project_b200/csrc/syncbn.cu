@@ -59,14 +59,15 @@ struct BnWork {
     uint2* partials;   // [strips][2C or 3C] packets
     uint2* ll_local;   // [2C] packets, exchange slot when world == 1
     uint2* locpk;      // [3C] packets: GPU-local totals handed from the slice owners to CTA 0 (conv-bias gradient)
-    unsigned long long* stamps;  // [kMaxGrid][4] globaltimer ns when SOD_DEBUG_TIMING is set, else null
+    unsigned long long* stamps;  // [kMaxGrid][8] globaltimer ns when SOD_DEBUG_TIMING is set, else null
+                                 // slots: 0 start, 1 phase-1 end, 2 exchange end, 3 end, 4 CTA reduced, 5 my hop-1 slice published, 6 (unused)
 };
 
 __device__ __forceinline__ void stamp(const BnWork& w, int slot) {
     if (w.stamps != nullptr && threadIdx.x == 0) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-        w.stamps[blockIdx.x * 4 + slot] = t;
+        w.stamps[blockIdx.x * 8 + slot] = t;
     }
 }
 
@@ -401,6 +402,7 @@ __device__ __forceinline__ void exchange(const BnGeom& g, const BnWork& w, const
             if (na > 16) st_packet_gpu(w.locpk + j, acc, tag);
         }
     }
+    stamp(w, 5);
     cbar();  // everyone has finished reading red[] (hop 1a) before it is overwritten
     for (int j = tid; j < nglob; j += kThreads) red[j] = collect(c, stats_off, w.ll_local, g.C, j, tag, timeout, fail);
     if (fail) {
@@ -483,6 +485,7 @@ __device__ __forceinline__ void exchange_moments(const BnGeom& g, const BnWork& 
             publish(c, use_mc, stats_off, w.ll_local, C, C + j, sq, tag);
         }
     }
+    stamp(w, 5);
     cbar();  // everyone has finished reading red[] (hop 1a) before it is overwritten
     for (int j = tid; j < C; j += kThreads) {
         float mean, var;
@@ -669,6 +672,7 @@ __global__ void __launch_bounds__(kBlock, 1) syncbn_fwd_kernel(const __grid_cons
         }
         stamp(prm.w, 1);
         cta_reduce<16>(a, L, red);
+        stamp(prm.w, 4);
         exchange_moments(g, prm.w, prm.c, prm.use_mc, prm.stats_off, call_tag(prm.tag, prm.epoch), red, s_raw, &s_fail);
         stamp(prm.w, 2);
         // ---- per-channel coefficients --------------------------------------------------------------------
@@ -936,6 +940,7 @@ __global__ void __launch_bounds__(kBlock, 1) syncbn_bwd_kernel(const __grid_cons
     }
     stamp(prm.w, 1);
     cta_reduce<NSTAT>(a, L, red);
+    stamp(prm.w, 4);
     {
         const float* sinv = s_b;
         float* dgamma = prm.dgamma;
@@ -1172,7 +1177,7 @@ extern "C" int sod_syncbn_fwd(const void* x, const void* pre_add, const void* re
     p.momentum = momentum; p.eps = eps; p.relu = relu; p.training = training;
     p.stats_off = stats_off; p.tag = seq; p.epoch = epoch;
     p.use_mc = (p.c.mc != 0) && !(flags & SOD_ALGO_NO_MULTIMEM);
-    if ((flags & SOD_DEBUG_TIMING) && workspace_bytes >= bn_ws_layout(channels, nullptr, nullptr) + kMaxGrid * 32)
+    if ((flags & SOD_DEBUG_TIMING) && workspace_bytes >= bn_ws_layout(channels, nullptr, nullptr) + kMaxGrid * 64)
         p.w.stamps = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + bn_ws_layout(channels, nullptr, nullptr));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     return SOD_DISPATCH_DTYPE(dtype, T, [&]() -> int {
@@ -1227,7 +1232,7 @@ extern "C" int sod_syncbn_bwd(const void* dy, const void* x, const void* pre_add
     p.cbias1 = conv_bias1; p.cbias2 = conv_bias2; p.dcbias1 = dconv_bias1; p.dcbias2 = dconv_bias2; p.cbias_dtype = conv_bias_dtype;
     const bool fold = conv_bias1 != nullptr || conv_bias2 != nullptr;
     p.use_mc = (p.c.mc != 0) && !(flags & SOD_ALGO_NO_MULTIMEM);
-    if ((flags & SOD_DEBUG_TIMING) && workspace_bytes >= bn_ws_layout(channels, nullptr, nullptr) + kMaxGrid * 32)
+    if ((flags & SOD_DEBUG_TIMING) && workspace_bytes >= bn_ws_layout(channels, nullptr, nullptr) + kMaxGrid * 64)
         p.w.stamps = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + bn_ws_layout(channels, nullptr, nullptr));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     return SOD_DISPATCH_DTYPE(dtype, T, [&]() -> int {

@@ -16,6 +16,8 @@ from . import _lib
 ENABLED = False     # switched on by the B200 engine (engine.Trainer)
 # the stem's MaxPool2d(3, 2, 1) through csrc/maxpool.cu (checked against torch on B200 in round 2; SOD_MAXPOOL=0 → torch op)
 MAXPOOL_ENABLED = os.environ.get("SOD_MAXPOOL", "1") == "1"
+# bias gradient of the convolutions that do not feed a BatchNorm as a deterministic column sum (SOD_COLSUM=0 → autograd's reduction)
+COLSUM_ENABLED = os.environ.get("SOD_COLSUM", "1") == "1"
 
 
 def _ok(x: torch.Tensor) -> bool:
@@ -133,3 +135,51 @@ def maxpool3x3s2(x: torch.Tensor) -> torch.Tensor | None:
     if not (MAXPOOL_ENABLED and _ok(x)):
         return None
     return _MaxPool3x3s2.apply(x)
+
+
+# ---- convolution whose bias gradient is a deterministic column sum (csrc/resample.cu: sod_colsum) ------------------------
+_colsum_ws: dict = {}
+
+
+def colsum(x: torch.Tensor) -> torch.Tensor:
+    """Σ over N, H, W of a channels-last [N,C,H,W] tensor → [C] (same dtype)"""
+    x = _rows(x)
+    n, c, h, w = x.shape
+    ws = _colsum_ws.get(x.device.index)
+    if ws is None:
+        ws = _colsum_ws[x.device.index] = torch.zeros(int(_lib.lib().sod_colsum_workspace_bytes()), dtype=torch.uint8, device=x.device)
+    out = torch.empty(c, dtype=x.dtype, device=x.device)
+    rc = _lib.lib().sod_colsum(x.data_ptr(), out.data_ptr(), n * h * w, c, _lib.dtype_code(x.dtype), ws.data_ptr(), ws.numel(),
+                               _lib.stream_ptr())
+    _lib.check(rc, "sod_colsum")
+    _lib.count_launch()
+    return out
+
+
+class _ConvBias(torch.autograd.Function):
+    """conv2d with bias (cuDNN fuses the bias add into the forward); backward = cuDNN dgrad/wgrad + `colsum` for the bias"""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, padding, dilation, groups):
+        y = torch.nn.functional.conv2d(x, weight, bias, stride, padding, dilation, groups)
+        ctx.conf = (stride, padding, dilation, groups)
+        ctx.save_for_backward(x if x.dtype == y.dtype else x.to(y.dtype), weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        stride, padding, dilation, groups = ctx.conf
+        dx, dw, _ = torch.ops.aten.convolution_backward(dy, x, weight, None, list(stride), list(padding), list(dilation), False, [0, 0],
+                                                        groups, [ctx.needs_input_grad[0], ctx.needs_input_grad[1], False])
+        db = colsum(dy).to(weight.dtype) if ctx.needs_input_grad[2] else None
+        return dx, dw, db, None, None, None, None
+
+
+def conv_bias(conv: torch.nn.Conv2d, x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch.Tensor | None:
+    """`conv(x)` with the bias gradient taken by `colsum`; None when the kernel does not cover the case"""
+    c = weight.shape[0]
+    if not (ENABLED and COLSUM_ENABLED and x.is_cuda and bias is not None and c % 8 == 0 and c <= 2048 and (c // 8) & (c // 8 - 1) == 0
+            and x.dtype in (torch.bfloat16, torch.float16, torch.float32) and weight.dtype == x.dtype and torch.is_grad_enabled()):
+        return None
+    return _ConvBias.apply(x, weight, bias, conv.stride, conv.padding, conv.dilation, conv.groups)

@@ -44,7 +44,7 @@ TRACE: list | None = None   # bench.py: when a list, every forward call appends 
 def _dev_state(device: torch.device) -> dict:
     st = _state.get(device.index)
     if st is None:
-        nbytes = int(_lib.lib().sod_syncbn_workspace_bytes(1, 2048)) + 8192    # + room for debug stamps
+        nbytes = int(_lib.lib().sod_syncbn_workspace_bytes(1, 2048)) + 16384   # + room for debug stamps (kMaxGrid x 8 x 8 bytes)
         st = {"ws": torch.zeros(nbytes, dtype=torch.uint8, device=device), "seq": 0,
               "epoch": torch.zeros(1, dtype=torch.int32, device=device), "graph": False, "idx": 0}
         _state[device.index] = st

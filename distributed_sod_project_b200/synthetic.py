@@ -19,3 +19,18 @@ def synth_batch(seed: int, n: int, size: int):
     m = ((rad[:, None, None] - d) / 2.0 + 0.5).clamp(0, 1)
     m = (m * 255).round() / 255
     return x, m[:, None].contiguous()
+
+
+def synth_eval_set(name: str, indices, batch_size: int, size: int):
+    """Deterministic synthetic evaluation set: yields (image [n,3,S,S] f32 CUDA, gt_u8 [n,S,S] uint8 CUDA) for the given
+    image indices (each index is one image, the same on whichever rank evaluates it)."""
+    import zlib
+    base = zlib.crc32(name.encode()) % 100000
+    idx = list(indices)
+    for i in range(0, len(idx), batch_size):
+        xs, gs = [], []
+        for j in idx[i:i + batch_size]:
+            x, m = synth_batch(base + j, 1, size)
+            xs.append(x)
+            gs.append((m[:, 0] * 255).round().to(torch.uint8))
+        yield torch.cat(xs).cuda(non_blocking=True), torch.cat(gs).cuda(non_blocking=True)

@@ -206,12 +206,18 @@ int sod_upsample2x_bilinear_bwd(const void* dy, void* dx, int n, int h, int w, i
 int sod_avgpool2x2_fwd(const void* x, void* y, int n, int h_out, int w_out, int c, int dtype, void* stream);
 int sod_avgpool2x2_bwd(const void* dy, void* dx, int n, int h_out, int w_out, int c, int dtype, void* stream);
 
-/* EXPERIMENTAL (exported, but the host layer keeps it off until it has been checked against torch on hardware):
- * MaxPool2d(kernel 3, stride 2, padding 1) of the ResNet stem (backbone/origin/resnet.py `maxpool`; `div_4` in
+/* Column sum of a channels-last matrix [rows, c] (c a power-of-two multiple of 8, ≤ 2048) into out[c] (same dtype, fp32
+ * accumulation, deterministic): the bias gradient Σ_rows dy of a convolution that does not feed a BatchNorm — the five
+ * `trans*` 1x1 convolutions of network/TestModel.py:32-36 — which autograd otherwise computes with a generic reduction.
+ * workspace: sod_colsum_workspace_bytes() bytes, zero-filled once, then owned by the library (one stream at a time). */
+size_t sod_colsum_workspace_bytes(void);
+int sod_colsum(const void* x, void* out, int64_t rows, int c, int dtype, void* workspace, size_t workspace_bytes, void* stream);
+
+/* MaxPool2d(kernel 3, stride 2, padding 1) of the ResNet stem (backbone/origin/resnet.py `maxpool`; `div_4` in
  * backbone/origin/from_origin.py:7-15), channels-last [N,H,W,C], C % 8 == 0; (h, w) = INPUT size, output
  * ((h-1)/2+1, (w-1)/2+1).  argmax: one byte per OUTPUT element (window position kh*3+kw), written by the forward and
  * read by the backward, which is a deterministic gather with fp32 accumulation.  Ties / NaN as torch: first maximum
- * in (kh, kw) scan order, NaN propagates. */
+ * in (kh, kw) scan order, NaN propagates.  (Checked against torch on B200 in round 2 and enabled by default.) */
 int sod_maxpool3x3s2_fwd(const void* x, void* y, void* argmax, int n, int h, int w, int c, int dtype, void* stream);
 int sod_maxpool3x3s2_bwd(const void* dy, const void* argmax, void* dx, int n, int h, int w, int c, int dtype, void* stream);
 

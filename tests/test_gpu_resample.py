@@ -105,3 +105,41 @@ def test_maxpool3x3s2_matches_torch(shape, dtype, ties):
             assert torch.equal(blocks._StemPool(3, 2, 1)(x1.detach()), y2.detach())
     finally:
         resample.MAXPOOL_ENABLED = old
+
+
+@pytest.mark.parametrize("shape", [(16, 64, 160, 160), (3, 8, 5, 7), (2, 2048, 3, 3), (1, 64, 1, 1), (4, 256, 20, 20)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_colsum_matches_torch_and_is_deterministic(shape, dtype):
+    from distributed_sod_project_b200 import resample
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(shape, generator=g).to(dtype).cuda().contiguous(memory_format=torch.channels_last)
+    got = resample.colsum(x)
+    want = x.double().sum(dim=(0, 2, 3))
+    tol = 1e-5 if dtype == torch.float32 else 2.0 ** -8
+    assert float((got.double() - want).abs().max()) <= tol * float(x.double().abs().sum(dim=(0, 2, 3)).max())
+    assert all(torch.equal(resample.colsum(x), got) for _ in range(3))
+
+
+def test_conv_with_colsum_bias_gradient_matches_autograd():
+    """the five `trans*` convolutions (1x1, 64 outputs, bias): forward identical, input / weight gradients cuDNN's, bias
+    gradient = deterministic column sum"""
+    from distributed_sod_project_b200 import resample
+    old, resample.ENABLED = resample.ENABLED, True
+    try:
+        for dtype, tol in ((torch.float32, 1e-5), (torch.bfloat16, 2e-2)):
+            conv = torch.nn.Conv2d(256, 64, 1).cuda().to(dtype).to(memory_format=torch.channels_last)
+            x = torch.randn(4, 256, 20, 20, device="cuda").to(dtype).contiguous(memory_format=torch.channels_last)
+            dy = torch.randn(4, 64, 20, 20, device="cuda").to(dtype).contiguous(memory_format=torch.channels_last)
+            res = []
+            for mine in (False, True):
+                xx = x.clone().requires_grad_(True)
+                w = conv.weight.detach().clone().requires_grad_(True); b = conv.bias.detach().clone().requires_grad_(True)
+                y = resample.conv_bias(conv, xx, w, b) if mine else torch.nn.functional.conv2d(xx, w, b)
+                assert y is not None
+                y.backward(dy)
+                res.append((y.detach(), xx.grad, w.grad, b.grad))
+            assert torch.equal(res[0][0], res[1][0])
+            for a, bb in zip(res[0][1:], res[1][1:]):
+                assert float((a.float() - bb.float()).abs().max()) <= tol * max(1.0, float(a.float().abs().max()))
+    finally:
+        resample.ENABLED = old

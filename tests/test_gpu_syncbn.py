@@ -251,4 +251,4 @@ def test_forward_statistics_survive_a_large_mean(mean, std, shape, with_bias):
     got_mean = bn.running_mean.double().cpu().numpy() / 0.1
     np.testing.assert_allclose(got_mean, ref["mean"], rtol=1e-6, atol=1e-6 * max(1.0, abs(mean)))
     extreme = abs(mean) / std > 500
-    np.testing.assert_allclose(y.double().cpu().numpy(), ref["ys"][0], rtol=0, atol=(4e-2 if with_bias else 2e-2) if extreme else 2e-3)
+    np.testing.assert_allclose(y.detach().double().cpu().numpy(), ref["ys"][0], rtol=0, atol=(4e-2 if with_bias else 2e-2) if extreme else 2e-3)

@@ -21,14 +21,27 @@ def _run(ngpus, overrides, port):
 
 def test_train_cli_single_gpu_multiscale(tmp_path):
     out = _run(1, {"epoch_num": 2, "synthetic_iters_per_epoch": 3, "batch_size": 4, "print_freq": 1, "save_freq": 0, "is_distributed": False,
-                   "size_list": [128, 192], "input_size": 192, "model": "cp_res50", "output_name": "output"}, 29701)
+                   "size_list": [128, 192], "input_size": 192, "model": "cp_res50", "output_name": "output", "synthetic_eval_images": 6}, 29701)
     assert "End Training" in out and out.count("[I:") == 6 and "Lr:0.0050000,0.0500000" in out
     ckpt = [l for l in out.splitlines() if "img/s" in l]
     assert len(ckpt) == 2
+    # the final evaluation over every test set of the config (reference train.py:273-275), GPU metrics
+    assert out.count("Results on the testset(") == 6 and "'MAE':" in out and "'SM':" in out
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_train_cli_two_gpus_graph():
     out = _run(2, {"epoch_num": 1, "synthetic_iters_per_epoch": 4, "batch_size": 8, "print_freq": 2, "save_freq": 0,
-                   "input_size": 128, "model": "res50", "cuda_graph": True}, 29702)
+                   "input_size": 128, "model": "res50", "cuda_graph": True, "synthetic_eval_images": 7}, 29702)
     assert "End Training" in out and out.count("[I:") == 2
+    assert out.count("Results on the testset(") == 6
+
+
+def test_train_cli_test_mode_evaluates_a_saved_checkpoint():
+    """resume_mode == "test" (the reference's DEFAULT, config.py:28): load the saved weights, evaluate, exit"""
+    common = {"epoch_num": 1, "synthetic_iters_per_epoch": 2, "batch_size": 4, "print_freq": 0, "save_freq": 1, "is_distributed": False,
+              "input_size": 96, "model": "res50", "output_name": "output_testmode", "synthetic_eval_images": 5, "val_freq": 1}
+    out = _run(1, dict(common, final_test=False), 29703)
+    assert out.count("Results on the valset(") == 1 and "Results on the testset(" not in out
+    out = _run(1, dict(common, resume_mode="test"), 29704)
+    assert "Loaded checkpoint" in out and out.count("Results on the testset(") == 6 and "[I:" not in out

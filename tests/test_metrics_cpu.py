@@ -14,21 +14,7 @@ def _load(golden):
     return g, [(g[f"pred{i}"], g[f"gt{i}"]) for i in range(n)]
 
 
-def emulate_kernels(p8, g8):
-    """what sod_saliency_head / sod_saliency_hist write for one image"""
-    h, w = p8.shape
-    gmax = int(g8.max())
-    gb = (2 * g8.astype(np.int64) > gmax) & (gmax > 0)
-    ys, xs = np.nonzero(gb)
-    head = np.array([p8.min(), p8.max(), gmax, 0, gb.sum(), ys.sum(), xs.sum(), 0], dtype=np.int64)
-    n_fg = max(int(gb.sum()), 1)
-    cy, cx = int(round(int(ys.sum()) / n_fg)) + 1, int(round(int(xs.sum()) / n_fg)) + 1
-    yy, xx = np.mgrid[0:h, 0:w]
-    q = (yy >= cy) * 2 + (xx >= cx)
-    k = p8.astype(np.int64) - int(p8.min())
-    hist = np.zeros((4, 2, 256), dtype=np.int64)
-    np.add.at(hist, (q.ravel(), gb.astype(np.int64).ravel(), k.ravel()), 1)
-    return head, hist
+emulate_kernels = om.emulate_kernels
 
 
 def test_oracle_matches_the_reference_classes(golden):

@@ -8,8 +8,8 @@ train.py:84-101) and the same construction order in `main_worker` (train.py:104-
 B200 engine (`distributed_sod_project_b200/engine.py`).  NCCL is still initialised — it bootstraps the symmetric-memory
 rendezvous — but no NCCL collective runs inside an iteration.
 
-Out of scope here: evaluation / metrics (`test`, `_test_process`), TensorBoard / xlsx recorders, dataset
-decoding.  When `user_config["synthetic"]` is set (or the dataset root is absent) batches come from
+Out of scope here: TensorBoard / xlsx recorders, dataset decoding.  Evaluation (`test`, `_test_process`) runs
+distributed with GPU metrics (distributed_sod_project_b200/evaluate.py, metrics.py) on synthetic test sets.  When `user_config["synthetic"]` is set (or the dataset root is absent) batches come from
 `synthetic.synth_batch`, which honours the dataloader's output contract, incl. the multi-scale `size_list` collate.
 """
 from __future__ import annotations
@@ -26,7 +26,8 @@ from config import user_config
 from distributed_sod_project_b200 import amp
 from distributed_sod_project_b200.checkpoint import resume_checkpoint, save_checkpoint
 from distributed_sod_project_b200.engine import Trainer
-from distributed_sod_project_b200.synthetic import synth_batch
+from distributed_sod_project_b200.evaluate import shard, test_process
+from distributed_sod_project_b200.synthetic import synth_batch, synth_eval_set
 from distributed_sod_project_b200.utils import (AvgMeter, check_mkdir, construct_exp_name, construct_path_dict, construct_print,
                                                 init_cudnn, write_data_to_file)
 
@@ -47,6 +48,30 @@ def init_process(ip, port, rank, world_size):
     os.environ["MASTER_PORT"] = port
     dist.init_process_group(backend="nccl", init_method="env://", world_size=world_size, rank=rank,
                             device_id=torch.device("cuda", rank % torch.cuda.device_count()))
+
+
+class SyntheticU8Loader:
+    """what the reference's DataLoader workers produce BEFORE `ToTensor` (utils/dataset.py:104-116): 8-bit HWC images and
+    8-bit masks at `in_size`, pinned; the tensor-side transforms and the multi-scale collate then run on the GPU
+    (distributed_sod_project_b200/pipeline.py)"""
+
+    def __init__(self, batch_size, iters, in_size, rank, epoch_seed=0):
+        self.bs, self.iters, self.in_size, self.rank, self.epoch = batch_size, iters, in_size, rank, epoch_seed
+
+    def set_epoch(self, epoch):
+        self.epoch = epoch
+
+    def __len__(self):
+        return self.iters
+
+    def __iter__(self):
+        for i in range(self.iters):
+            seed = 1234 + self.rank + 1000 * (self.epoch * self.iters + i)
+            g = torch.Generator().manual_seed(seed)
+            img = torch.randint(0, 256, (self.bs, self.in_size, self.in_size, 3), generator=g, dtype=torch.uint8)
+            _, m = synth_batch(seed, self.bs, self.in_size)
+            mask = (m[:, 0] * 255).round().to(torch.uint8)
+            yield img.pin_memory(), mask.pin_memory(), [f"synthetic_{self.epoch}_{i}_{k}" for k in range(self.bs)]
 
 
 class SyntheticLoader:
@@ -86,12 +111,18 @@ def main_worker(local_rank, ngpus_per_node, world_size, args, exp_name, path_con
         # repository covers: refuse loudly rather than silently train on noise
         raise NotImplementedError('user_config["synthetic"] is False, but only the synthetic loader is wired into this train.py; '
                                   "feed real batches through distributed_sod_project_b200.pipeline.preprocess_batch instead")
-    loader = SyntheticLoader(batch_size_single_gpu, cfg.get("synthetic_iters_per_epoch", 20), cfg["input_size"],
-                             cfg["size_list"], local_rank)
+    use_pipeline = cfg.get("synthetic_uint8", True)
+    if use_pipeline:
+        # uint8 batches from the (here: synthetic) workers, pinned → H2D and ToTensor / Normalize / multi-scale
+        # collate as one GPU kernel, one batch ahead of the iteration (reference: BackgroundGenerator, train.py:285)
+        from distributed_sod_project_b200.pipeline import DevicePrefetcher
+        source = SyntheticU8Loader(batch_size_single_gpu, cfg.get("synthetic_iters_per_epoch", 20), cfg["input_size"], local_rank)
+        loader = DevicePrefetcher(source, size_list=cfg["size_list"], seed=0)
+        loader.set_epoch = lambda e, _l=loader, _s=source: (_s.set_epoch(e), _l.rng.seed(e))
+    else:
+        loader = SyntheticLoader(batch_size_single_gpu, cfg.get("synthetic_iters_per_epoch", 20), cfg["input_size"],
+                                 cfg["size_list"], local_rank)
     total_iter_num = cfg["epoch_num"] * len(loader)
-    if cfg["resume_mode"] == "test":
-        construct_print("evaluation is outside the B200 hot path (SURVEY §2); nothing to do")
-        return
 
     dtype = _DTYPES[cfg.get("dtype", "bf16")] if cfg["use_amp"] else torch.float32
     trainer = Trainer(model_name=cfg["model"], lr=cfg["lr"], momentum=cfg["momentum"], weight_decay=cfg["weight_decay"],
@@ -105,6 +136,30 @@ def main_worker(local_rank, ngpus_per_node, world_size, args, exp_name, path_con
     if local_rank == 0:
         construct_print(f"optimizer = {trainer.optimizer}")
         construct_print(f"scheduler = {scheduler}")
+
+    def test(mode="test"):
+        """reference train.py:338-369: every data set of `te_data_list` (mode "val": `val_data_path`) through the model;
+        here every rank evaluates its shard and the metrics are reduced over the ranks (evaluate.py)"""
+        names = cfg["rgb_data"]["val_data_path"] if mode == "val" else cfg["rgb_data"]["te_data_list"]
+        total_results = {}
+        for data_name in names:
+            n_img = cfg.get("synthetic_eval_images", 32)
+            mine = list(shard(n_img))
+            batches = synth_eval_set(data_name, mine, batch_size_single_gpu, cfg["input_size"])
+            results = test_process(trainer.model, batches, length=n_img)
+            msg = f"Results on the {mode}set({data_name}: synthetic, {n_img} images over {max(world_size, 1)} rank(s)):\n{results}"
+            if local_rank == 0:
+                write_data_to_file(msg, path_config["te_log"])
+                construct_print(msg)
+            total_results[data_name.upper()] = results
+        return total_results
+
+    if cfg["resume_mode"] == "test":                                  # reference train.py:160-172: load the weights, evaluate, stop
+        resume_checkpoint(model=trainer.model, load_path=path_config["final_full_net"], mode="onlynet", local_rank=local_rank)
+        test(mode="test")
+        if dist.is_initialized():
+            dist.destroy_process_group()
+        return
 
     start_epoch = 0
     if cfg["resume_mode"] == "train":
@@ -126,8 +181,8 @@ def main_worker(local_rank, ngpus_per_node, world_size, args, exp_name, path_con
             curr_iter = curr_epoch * len(loader) + batch_id
             if cfg["sche_usebatch"]:
                 scheduler.step(trainer.optimizer, curr_epoch=curr_iter)
-            inputs = inputs.cuda(non_blocking=True)                                      # train.py:291-292
-            masks = masks.cuda(non_blocking=True)
+            inputs = inputs.cuda(non_blocking=True)                                      # train.py:291-292 (no-ops on the
+            masks = masks.cuda(non_blocking=True)                                        # pipeline path: already on the device)
             want_log = local_rank == 0 and cfg["print_freq"] > 0 and (curr_iter + 1) % cfg["print_freq"] == 0
             reduced, items, _ = trainer.forward_backward_update(inputs, masks, report=want_log)
             # reference train.py:311 updates the running average every iteration; here that costs no host sync
@@ -148,11 +203,15 @@ def main_worker(local_rank, ngpus_per_node, world_size, args, exp_name, path_con
         if local_rank == 0:
             n_img = len(loader) * batch_size_single_gpu * max(world_size, 1)
             construct_print(f"epoch {curr_epoch}: {time.time() - t0:.2f}s, {n_img / (time.time() - t0):.1f} img/s")
+        if cfg["val_freq"] > 0 and (curr_epoch + 1) % cfg["val_freq"] == 0:      # train.py:254-255 (there: rank 0 only)
+            test(mode="val")
         if (cfg["save_freq"] > 0 and (curr_epoch + 1) % cfg["save_freq"] == 0) or curr_epoch == cfg["epoch_num"] - 1:
             # every rank enters (the sharded momentum is gathered collectively), rank 0 writes, all leave through a barrier
             save_checkpoint(model=trainer.model, optimizer=trainer.optimizer, amp=amp if cfg["use_amp"] else None,
                             exp_name=exp_name, current_epoch=curr_epoch + 1, full_net_path=path_config["final_full_net"],
                             state_net_path=path_config["final_state_net"], write=local_rank == 0)   # utils/pipeline_ops.py:46-78
+    if cfg.get("final_test", True):
+        test(mode="test")                                                      # train.py:273-275
     construct_print("End Training...")
     trainer.check_errors()
     if dist.is_initialized():
