@@ -15,6 +15,7 @@ SOD_F32, SOD_BF16, SOD_F16 = 0, 1, 2
 SOD_MAX_WORLD = 8
 SOD_MAX_SEGMENTS = 16
 SOD_SEG_FROZEN = 1
+SOD_SEG_GRAD16 = 2
 SOD_SGD_ZERO_GRAD = 1
 SOD_ALGO_NO_MULTIMEM = 2
 SOD_BN_ACCUMULATE_PARAM_GRADS = 8
@@ -24,7 +25,7 @@ SOD_BN_L2_HINTS = 64
 SOD_BN_LAUNCH_COOP = 128
 SOD_BN_LAUNCH_PDL = 256
 SOD_GATHER_MAX_ITEMS = 160
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 
 class SodError(RuntimeError):
@@ -58,7 +59,7 @@ _PROTOTYPES = {
     "sod_comm_flag_bytes": (C.c_size_t, []),
     "sod_sgd_momentum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                    C.POINTER(sod_sgd_segment), C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_void_p]),
-    "sod_allreduce_sgd": (C.c_int, [C.POINTER(sod_comm), C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int64,
+    "sod_allreduce_sgd": (C.c_int, [C.POINTER(sod_comm), C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int64,
                                     C.POINTER(sod_sgd_segment), C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_void_p]),
     "sod_grad_gather16": (C.c_int, [C.POINTER(sod_gather_item), C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
     "sod_grad_merge_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),

@@ -244,7 +244,20 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, T*
 #pragma unroll
     for (int k = 0; k < 8; ++k) a[k] = 0.f;
     if (r0 < R) {
-        for (long long r = static_cast<long long>(blockIdx.x) * R + r0; r < rows; r += static_cast<long long>(gridDim.x) * R) {
+        // four independent 16-byte loads in flight per thread (the loop is latency bound otherwise: 1.3 TB/s measured with one)
+        const long long step = static_cast<long long>(gridDim.x) * R;
+        long long r = static_cast<long long>(blockIdx.x) * R + r0;
+        for (; r + 3 * step < rows; r += 4 * step) {
+            typename IO<T>::Raw q0 = IO<T>::load_raw(x + r * C + l * 8);
+            typename IO<T>::Raw q1 = IO<T>::load_raw(x + (r + step) * C + l * 8);
+            typename IO<T>::Raw q2 = IO<T>::load_raw(x + (r + 2 * step) * C + l * 8);
+            typename IO<T>::Raw q3 = IO<T>::load_raw(x + (r + 3 * step) * C + l * 8);
+            float v0[8], v1[8], v2[8], v3[8];
+            IO<T>::unpack(q0, v0); IO<T>::unpack(q1, v1); IO<T>::unpack(q2, v2); IO<T>::unpack(q3, v3);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] += (v0[k] + v1[k]) + (v2[k] + v3[k]);
+        }
+        for (; r < rows; r += step) {
             float v[8];
             IO<T>::load8(x + r * C + l * 8, v);
 #pragma unroll

@@ -57,9 +57,13 @@ __device__ __forceinline__ float seg_lr(const SegTable& t, const float* lr_dev, 
 
 struct SegCursor {
     int s = 0;
-    __device__ __forceinline__ bool find(const SegTable& t, long long vec) {
+    // segment containing `vec` (any kind), or false when it lies in a gap / behind the last segment
+    __device__ __forceinline__ bool locate(const SegTable& t, long long vec) {
         while (s < t.n && vec >= t.end[s]) ++s;
-        return s < t.n && vec >= t.begin[s] && !(t.flags[s] & SOD_SEG_FROZEN);
+        return s < t.n && vec >= t.begin[s];
+    }
+    __device__ __forceinline__ bool find(const SegTable& t, long long vec) {
+        return locate(t, vec) && !(t.flags[s] & SOD_SEG_FROZEN);
     }
 };
 
@@ -99,17 +103,26 @@ __global__ void __launch_bounds__(kThreads) sgd_local_kernel(float4* __restrict_
     for (long long i0 = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i0 < nvec; i0 += stride * kUnroll) {
         float4 gv[kUnroll], pv[kUnroll], vv[kUnroll];
         int sidx[kUnroll];
+        bool only16[kUnroll];
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
             const long long i = i0 + u * stride;
             sidx[u] = -1;
+            only16[u] = false;
             if (i < nvec) {
-                gv[u] = g[i];
-                if (g16 != nullptr) {   // gradients autograd left in bf16: fold them in here (the "cast" of amp O1)
-                    const float4 h = bf16x4_to_f32(g16[i]);
-                    gv[u].x += h.x; gv[u].y += h.y; gv[u].z += h.z; gv[u].w += h.w;
+                const bool in_seg = cur.locate(segs, i);
+                // SOD_SEG_GRAD16: the gradient of this range exists in bf16 only — the fp32 buffer is neither read nor cleared
+                only16[u] = in_seg && g16 != nullptr && (segs.flags[cur.s] & SOD_SEG_GRAD16);
+                if (only16[u]) {
+                    gv[u] = bf16x4_to_f32(g16[i]);
+                } else {
+                    gv[u] = g[i];
+                    if (g16 != nullptr) {   // gradients autograd left in bf16: fold them in here (the "cast" of amp O1)
+                        const float4 h = bf16x4_to_f32(g16[i]);
+                        gv[u].x += h.x; gv[u].y += h.y; gv[u].z += h.z; gv[u].w += h.w;
+                    }
                 }
-                if (!skip && cur.find(segs, i)) {
+                if (!skip && in_seg && !(segs.flags[cur.s] & SOD_SEG_FROZEN)) {
                     sidx[u] = cur.s;
                     pv[u] = p[i];
                     vv[u] = v[i];
@@ -129,7 +142,7 @@ __global__ void __launch_bounds__(kThreads) sgd_local_kernel(float4* __restrict_
                     if (shadow != nullptr) shadow[i] = f32x4_to_bf16(pv[u]);
                 }
                 if (zero_grad) {
-                    g[i] = zero;
+                    if (!only16[u]) g[i] = zero;
                     if (g16 != nullptr) g16[i] = make_uint2(0u, 0u);
                 }
             }
@@ -225,13 +238,31 @@ __device__ __forceinline__ void broadcast_vec(const CommDev& c, uint64_t byte_of
     }
 }
 
+// bf16 gradients on the wire: 4 elements = 8 bytes per rank, summed in fp32 in rank order (exact: no rounding of the sum,
+// unlike a bf16 multimem reduction), so every owner obtains the same value it would from an fp32 exchange of the same data
+__device__ __forceinline__ float4 reduce_vec16(const CommDev& c, uint64_t byte_off) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint2 raw[SOD_MAX_WORLD];
+#pragma unroll
+    for (int q = 0; q < SOD_MAX_WORLD; ++q)
+        if (q < c.world) raw[q] = ld_relaxed_sys_v2(reinterpret_cast<const void*>(c.peer[q] + byte_off));
+#pragma unroll
+    for (int q = 0; q < SOD_MAX_WORLD; ++q)
+        if (q < c.world) {
+            const float4 t = bf16x4_to_f32(raw[q]);
+            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        }
+    return acc;
+}
+
 template <bool kMulticast>
 __global__ void __launch_bounds__(kThreads) allreduce_sgd_kernel(const __grid_constant__ CommDev c, uint64_t grad_off,
                                                                  uint64_t param_off, float4* __restrict__ mom,
                                                                  long long nvec, const __grid_constant__ SegTable segs,
                                                                  float scale, const uint32_t* found_inf,
                                                                  int zero_grad, uint2* __restrict__ shadow,
-                                                                 const float* __restrict__ lr_dev) {
+                                                                 const float* __restrict__ lr_dev, uint64_t grad16_off,
+                                                                 int has_grad16) {
     const bool skip = (found_inf != nullptr && *found_inf != 0);  // caller guarantees identical on all ranks
     // every rank's backward has finished writing its gradients
     if (!comm_block_barrier(c, 0, blockIdx.x)) return;
@@ -246,16 +277,24 @@ __global__ void __launch_bounds__(kThreads) allreduce_sgd_kernel(const __grid_co
         SegCursor cur;
         for (long long i0 = lo + static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i0 < hi; i0 += stride * kUnroll) {
             float4 gv[kUnroll];
+            int sidx[kUnroll];
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
                 const long long i = i0 + u * stride;
-                if (i < hi) gv[u] = reduce_vec<kMulticast>(c, grad_off + static_cast<uint64_t>(i) * 16u);
+                sidx[u] = -1;
+                if (i < hi && cur.find(segs, i)) {        // frozen ranges and gaps are never consumed: not even reduced
+                    sidx[u] = cur.s;
+                    if (has_grad16 && (segs.flags[cur.s] & SOD_SEG_GRAD16))
+                        gv[u] = reduce_vec16(c, grad16_off + static_cast<uint64_t>(i) * 8u);
+                    else
+                        gv[u] = reduce_vec<kMulticast>(c, grad_off + static_cast<uint64_t>(i) * 16u);
+                }
             }
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
                 const long long i = i0 + u * stride;
-                if (i < hi && cur.find(segs, i)) {
-                    const int s = cur.s;
+                if (sidx[u] >= 0) {
+                    const int s = sidx[u];
                     float4 pv = p_local[i], vv = mom[i];
                     const float4 gs = make_float4(gv[u].x * scale, gv[u].y * scale, gv[u].z * scale, gv[u].w * scale);
                     sgd_update(pv, vv, gs, seg_lr(segs, lr_dev, s), segs.wd[s], segs.mu[s]);
@@ -273,12 +312,19 @@ __global__ void __launch_bounds__(kThreads) allreduce_sgd_kernel(const __grid_co
         // barrier it is safe to clear those gradients, and the parameters that landed there are final — refresh the
         // local bf16 shadow from them
         float4* g_local = reinterpret_cast<float4*>(c.peer[c.rank] + grad_off);
+        uint2* g16_local = has_grad16 ? reinterpret_cast<uint2*>(c.peer[c.rank] + grad16_off) : nullptr;
         const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int q = 0; q < c.world; ++q) {
             const long long qlo = shard * q;
             const long long qhi = (qlo + shard < nvec) ? qlo + shard : nvec;
+            SegCursor cur;                                   // indices restart for every shard
             for (long long i = qlo + static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x; i < qhi; i += stride) {
-                if (zero_grad) g_local[i] = zero;
+                const bool in_seg = cur.locate(segs, i);
+                const bool only16 = in_seg && has_grad16 && (segs.flags[cur.s] & SOD_SEG_GRAD16);
+                if (zero_grad) {
+                    if (!only16) g_local[i] = zero;
+                    if (g16_local != nullptr) g16_local[i] = make_uint2(0u, 0u);
+                }
                 if (shadow != nullptr && !skip) shadow[i] = f32x4_to_bf16(p_local[i]);
             }
         }
@@ -429,9 +475,9 @@ extern "C" int sod_grad_merge_bf16(float* grad, void* grad16, int64_t n, void* s
     return static_cast<int>(cudaGetLastError());
 }
 
-extern "C" int sod_allreduce_sgd(const sod_comm* comm, uint64_t grad_off, uint64_t param_off, float* mom, void* shadow16,
-                                 int64_t n, const sod_sgd_segment* segs, int nseg, const float* lr_dev, float inv_scale,
-                                 const uint32_t* found_inf, int flags, void* stream) {
+extern "C" int sod_allreduce_sgd(const sod_comm* comm, uint64_t grad_off, uint64_t grad16_off, uint64_t param_off, float* mom,
+                                 void* shadow16, int64_t n, const sod_sgd_segment* segs, int nseg, const float* lr_dev,
+                                 float inv_scale, const uint32_t* found_inf, int flags, void* stream) {
     using namespace sod;
     SOD_CHECK_ARG(comm && mom && n > 0, SOD_EINVAL);
     SOD_CHECK_ARG((n & 3) == 0 && aligned16(mom) && (grad_off & 15) == 0 && (param_off & 15) == 0, SOD_EALIGN);
@@ -441,6 +487,11 @@ extern "C" int sod_allreduce_sgd(const sod_comm* comm, uint64_t grad_off, uint64
     SOD_CHECK_ARG(grad_off >= sod_comm_flag_bytes() && param_off >= sod_comm_flag_bytes(), SOD_ECOMM);
     SOD_CHECK_ARG(grad_off + static_cast<uint64_t>(n) * 4 <= comm->arena_bytes &&
                       param_off + static_cast<uint64_t>(n) * 4 <= comm->arena_bytes, SOD_ECOMM);
+    const int has16 = grad16_off != 0 ? 1 : 0;
+    if (has16) {
+        SOD_CHECK_ARG((grad16_off & 15) == 0, SOD_EALIGN);
+        SOD_CHECK_ARG(grad16_off >= sod_comm_flag_bytes() && grad16_off + static_cast<uint64_t>(n) * 2 <= comm->arena_bytes, SOD_ECOMM);
+    }
     SegTable t;
     rc = make_seg_table(segs, nseg, n, t);
     if (rc != SOD_OK) return rc;
@@ -454,10 +505,10 @@ extern "C" int sod_allreduce_sgd(const sod_comm* comm, uint64_t grad_off, uint64
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (mc)
         allreduce_sgd_kernel<true><<<grid, kThreads, 0, s>>>(c, grad_off, param_off, reinterpret_cast<float4*>(mom), nvec, t,
-                                                             scale, found_inf, zg, reinterpret_cast<uint2*>(shadow16), lr_dev);
+                                                             scale, found_inf, zg, reinterpret_cast<uint2*>(shadow16), lr_dev, grad16_off, has16);
     else
         allreduce_sgd_kernel<false><<<grid, kThreads, 0, s>>>(c, grad_off, param_off, reinterpret_cast<float4*>(mom), nvec, t,
-                                                              scale, found_inf, zg, reinterpret_cast<uint2*>(shadow16), lr_dev);
+                                                              scale, found_inf, zg, reinterpret_cast<uint2*>(shadow16), lr_dev, grad16_off, has16);
     return static_cast<int>(cudaGetLastError());
 }
 

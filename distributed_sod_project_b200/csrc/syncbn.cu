@@ -188,23 +188,30 @@ __device__ __forceinline__ void publish(const CommDev& c, int use_mc, uint64_t s
 __device__ __forceinline__ const void* slot_of(const CommDev& c, uint64_t stats_off, int C, int q, int entry) {
     return reinterpret_cast<const void*>(c.peer[c.rank] + stats_off + (static_cast<uint64_t>(q) * 2u * C + entry) * 8u);
 }
-// The W per-rank packets of one entry are requested TOGETHER (independent loads in flight: one L2 round trip instead
-// of W serialized ones — at world 8 that was ≈5 µs per launch); only packets whose tag has not arrived are polled.
-// Values are summed in rank order, so every rank obtains bit-identical statistics.
+// The W per-rank packets of one entry are requested TOGETHER (independent loads in flight: one round trip instead of W
+// serialized ones — at world 8 that was ≈5 µs per launch), and whatever has not arrived is re-requested together, round
+// after round.  Values are summed by the caller in rank order, so every rank obtains bit-identical statistics.
 __device__ __forceinline__ void collect_all(const CommDev& c, uint64_t stats_off, int C, int entry, uint32_t tag,
                                             unsigned long long timeout, int& fail, float (&val)[SOD_MAX_WORLD]) {
     uint2 v[SOD_MAX_WORLD];
 #pragma unroll
     for (int q = 0; q < SOD_MAX_WORLD; ++q)
         if (q < c.world) v[q] = ld_relaxed_sys_v2(slot_of(c, stats_off, C, q, entry));
+    const long long t0 = clock64();
+    for (;;) {
+        bool late = false;
 #pragma unroll
-    for (int q = 0; q < SOD_MAX_WORLD; ++q) {
-        val[q] = 0.f;
-        if (q < c.world)
-            val[q] = (v[q].y == tag) ? __uint_as_float(v[q].x) : wait_packet_sys(slot_of(c, stats_off, C, q, entry), tag, timeout, fail);
+        for (int q = 0; q < SOD_MAX_WORLD; ++q) late |= (q < c.world) && (v[q].y != tag);
+        if (!late) break;
+#pragma unroll
+        for (int q = 0; q < SOD_MAX_WORLD; ++q)
+            if (q < c.world && v[q].y != tag) v[q] = ld_relaxed_sys_v2(slot_of(c, stats_off, C, q, entry));
+        if (static_cast<unsigned long long>(clock64() - t0) > timeout) { fail = 1; break; }
     }
+#pragma unroll
+    for (int q = 0; q < SOD_MAX_WORLD; ++q) val[q] = (q < c.world) ? __uint_as_float(v[q].x) : 0.f;
 }
-// two entries at once (forward: mean and M2 of one channel): all 2W packets are requested before any is examined
+// two entries at once (forward: mean and M2 of one channel): all 2W packets travel together
 __device__ __forceinline__ void collect_pair(const CommDev& c, uint64_t stats_off, int C, int e0, int e1, uint32_t tag,
                                              unsigned long long timeout, int& fail, float (&v0)[SOD_MAX_WORLD],
                                              float (&v1)[SOD_MAX_WORLD]) {
@@ -215,13 +222,23 @@ __device__ __forceinline__ void collect_pair(const CommDev& c, uint64_t stats_of
             a[q] = ld_relaxed_sys_v2(slot_of(c, stats_off, C, q, e0));
             b[q] = ld_relaxed_sys_v2(slot_of(c, stats_off, C, q, e1));
         }
+    const long long t0 = clock64();
+    for (;;) {
+        bool late = false;
+#pragma unroll
+        for (int q = 0; q < SOD_MAX_WORLD; ++q) late |= (q < c.world) && (a[q].y != tag || b[q].y != tag);
+        if (!late) break;
+#pragma unroll
+        for (int q = 0; q < SOD_MAX_WORLD; ++q) {
+            if (q < c.world && a[q].y != tag) a[q] = ld_relaxed_sys_v2(slot_of(c, stats_off, C, q, e0));
+            if (q < c.world && b[q].y != tag) b[q] = ld_relaxed_sys_v2(slot_of(c, stats_off, C, q, e1));
+        }
+        if (static_cast<unsigned long long>(clock64() - t0) > timeout) { fail = 1; break; }
+    }
 #pragma unroll
     for (int q = 0; q < SOD_MAX_WORLD; ++q) {
-        v0[q] = 0.f; v1[q] = 0.f;
-        if (q < c.world) {
-            v0[q] = (a[q].y == tag) ? __uint_as_float(a[q].x) : wait_packet_sys(slot_of(c, stats_off, C, q, e0), tag, timeout, fail);
-            v1[q] = (b[q].y == tag) ? __uint_as_float(b[q].x) : wait_packet_sys(slot_of(c, stats_off, C, q, e1), tag, timeout, fail);
-        }
+        v0[q] = (q < c.world) ? __uint_as_float(a[q].x) : 0.f;
+        v1[q] = (q < c.world) ? __uint_as_float(b[q].x) : 0.f;
     }
 }
 __device__ __forceinline__ float collect(const CommDev& c, uint64_t stats_off, const uint2* ll_local, int C, int entry,
@@ -383,16 +400,27 @@ __device__ __forceinline__ void exchange(const BnGeom& g, const BnWork& w, const
             const int t = lane + 32 * u;
             if (t < strips) v[u] = ld_packet_gpu(w.partials + static_cast<size_t>(t) * n16 + j);
         }
-        float acc = 0.f;
+        // packets that have not arrived yet are re-requested TOGETHER, round after round (a lane holds up to 5 of them:
+        // polling them one after the other would chain that many L2 round trips behind the slowest CTA)
+        {
+            const long long t0 = clock64();
+            for (;;) {
+                bool late = false;
 #pragma unroll
-        for (int u = 0; u < kMaxPer; ++u) {
-            const int t = lane + 32 * u;
-            if (t < strips) {
-                float val = __uint_as_float(v[u].x);
-                if (v[u].y != tag) val = wait_packet_gpu(w.partials + static_cast<size_t>(t) * n16 + j, tag, timeout, fail);
-                acc += val;
+                for (int u = 0; u < kMaxPer; ++u) late |= (lane + 32 * u < strips) && (v[u].y != tag);
+                if (!__any_sync(0xffffffffu, late)) break;
+#pragma unroll
+                for (int u = 0; u < kMaxPer; ++u) {
+                    const int t = lane + 32 * u;
+                    if (t < strips && v[u].y != tag) v[u] = ld_packet_gpu(w.partials + static_cast<size_t>(t) * n16 + j);
+                }
+                if (static_cast<unsigned long long>(clock64() - t0) > timeout) { fail = 1; break; }
             }
         }
+        float acc = 0.f;
+#pragma unroll
+        for (int u = 0; u < kMaxPer; ++u)
+            if (lane + 32 * u < strips) acc += __uint_as_float(v[u].x);
         acc = warp_sum(acc);
         if (lane == 0) {
             if (j < nglob) {
@@ -459,6 +487,22 @@ __device__ __forceinline__ void exchange_moments(const BnGeom& g, const BnWork& 
                 vq[u] = ld_packet_gpu(w.partials + static_cast<size_t>(t) * n16 + C + j);
             }
         }
+        {   // late packets are re-requested together, round after round (see exchange())
+            const long long t0 = clock64();
+            for (;;) {
+                bool late = false;
+#pragma unroll
+                for (int u = 0; u < kMaxPer; ++u) late |= (lane + 32 * u < strips) && (vm[u].y != tag || vq[u].y != tag);
+                if (!__any_sync(0xffffffffu, late)) break;
+#pragma unroll
+                for (int u = 0; u < kMaxPer; ++u) {
+                    const int t = lane + 32 * u;
+                    if (t < strips && vm[u].y != tag) vm[u] = ld_packet_gpu(w.partials + static_cast<size_t>(t) * n16 + j);
+                    if (t < strips && vq[u].y != tag) vq[u] = ld_packet_gpu(w.partials + static_cast<size_t>(t) * n16 + C + j);
+                }
+                if (static_cast<unsigned long long>(clock64() - t0) > timeout) { fail = 1; break; }
+            }
+        }
         float m[kMaxPer], q2[kMaxPer], nt[kMaxPer];
         float sm = 0.f;
 #pragma unroll
@@ -466,8 +510,8 @@ __device__ __forceinline__ void exchange_moments(const BnGeom& g, const BnWork& 
             const int t = lane + 32 * u;
             m[u] = 0.f; q2[u] = 0.f; nt[u] = 0.f;
             if (t < strips) {
-                m[u] = (vm[u].y == tag) ? __uint_as_float(vm[u].x) : wait_packet_gpu(w.partials + static_cast<size_t>(t) * n16 + j, tag, timeout, fail);
-                q2[u] = (vq[u].y == tag) ? __uint_as_float(vq[u].x) : wait_packet_gpu(w.partials + static_cast<size_t>(t) * n16 + C + j, tag, timeout, fail);
+                m[u] = __uint_as_float(vm[u].x);
+                q2[u] = __uint_as_float(vq[u].x);
                 nt[u] = strip_rows(g, t);
                 sm = fmaf(nt[u], m[u], sm);
             }

@@ -32,7 +32,14 @@ _ALIGN = 64  # elements; keeps every tensor view 256-byte aligned and every segm
 class FlatParams:
     """Group-major flat storage for a set of parameters."""
 
-    def __init__(self, groups: list[list[nn.Parameter]], leftovers: list[nn.Parameter]):
+    def __init__(self, groups: list[list[nn.Parameter]], leftovers: list[nn.Parameter], bf16_grad_ids: set | None = None):
+        """`bf16_grad_ids`: ids of the parameters whose gradient will exist in bf16 only once the amp shadow is installed
+        (convolution weights / biases).  Inside every bucket those come first, so that each bucket is at most two
+        contiguous ranges — [bf16-gradient part | fp32-gradient part] — and the kernels can take the gradient of the
+        first from the bf16 buffer alone (SOD_SEG_GRAD16)."""
+        bf16_grad_ids = bf16_grad_ids or set()
+        groups = [sorted(g, key=lambda p: id(p) not in bf16_grad_ids) for g in groups]       # stable: order kept inside each part
+        leftovers = sorted(leftovers, key=lambda p: id(p) not in bf16_grad_ids)
         self.groups, self.leftovers = groups, leftovers
         all_params = [p for g in groups for p in g] + leftovers
         if not all_params:
@@ -43,19 +50,23 @@ class FlatParams:
         self.device = dev
         self.slots: list[tuple[nn.Parameter, int]] = []      # (param, element offset)
         self.ranges: list[tuple[int, int]] = []               # per group [begin, end), then leftovers
+        self.splits: list[int] = []                           # per bucket: end of its bf16-gradient part
         off = 0
         for bucket in [*groups, leftovers]:
-            begin = off
+            begin = mid = off
             for p in bucket:
                 self.slots.append((p, off))
                 off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+                if id(p) in bf16_grad_ids:
+                    mid = off
             self.ranges.append((begin, off))
+            self.splits.append(mid)
         self.numel = off
         self.param = torch.zeros(off, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(off, dtype=torch.float32, device=dev)
         self.mom = torch.zeros(off, dtype=torch.float32, device=dev)
         self.arena = None          # set by DistributedDataParallel when world > 1
-        self.param_off = self.grad_off = 0
+        self.param_off = self.grad_off = self.grad16_off = 0
         self.shadow16: torch.Tensor | None = None   # bf16 copy of `param`, refreshed by the fused step (amp O1 shadow)
         self.grad16: torch.Tensor | None = None     # bf16 gradients autograd accumulates for the shadowed tensors
         # bf16 shadow leaves the convolutions consume (amp._install_shadow_weights): (leaf, element offset, steal)
@@ -115,6 +126,15 @@ class FlatParams:
         self.param, self.grad = new_p, new_g
         self.arena, self.param_off, self.grad_off = arena, param_off, grad_off
         self._bind(copy_from_params=False)
+        if self.grad16 is not None:
+            # the bf16 gradients cross NVLink as they are (csrc/sgd.cu reduce_vec16): they have to be peer-readable too
+            self.grad16_off = arena.alloc(2 * self.numel)
+            new16 = arena.view(self.grad16_off, self.numel, self.grad16.dtype)
+            new16.copy_(self.grad16)
+            self.grad16 = new16
+            for leaf, off, steal in self.shadow_leaves:
+                if not steal and leaf.requires_grad:
+                    leaf.grad = self._view(self.grad16, off, leaf)
         self.refresh_shadow()
 
     def momentum_view(self, p: nn.Parameter) -> torch.Tensor:
@@ -150,11 +170,13 @@ class FusedSGD(Optimizer):
             raise _lib.SodError("nesterov momentum is not on the reference's hot path (config.py:65 nesterov=False)")
         defaults = dict(lr=lr, momentum=momentum, weight_decay=weight_decay, nesterov=False, dampening=0)
         super().__init__(params, defaults)
-        if len(self.param_groups) > _lib.SOD_MAX_SEGMENTS - 1:
-            raise _lib.SodError(f"at most {_lib.SOD_MAX_SEGMENTS - 1} parameter groups")
+        if 2 * (len(self.param_groups) + 1) > _lib.SOD_MAX_SEGMENTS:
+            raise _lib.SodError(f"at most {_lib.SOD_MAX_SEGMENTS // 2 - 1} parameter groups")
         grouped = {id(p) for g in self.param_groups for p in g["params"]}
         leftovers = [p for p in model.parameters() if id(p) not in grouped] if model is not None else []
-        self.flat = FlatParams([list(g["params"]) for g in self.param_groups], leftovers)
+        conv_ids = {id(p) for m in model.modules() if isinstance(m, nn.Conv2d) for p in (m.weight, m.bias) if p is not None} \
+            if model is not None else set()
+        self.flat = FlatParams([list(g["params"]) for g in self.param_groups], leftovers, bf16_grad_ids=conv_ids)
         for p, _ in self.flat.slots:
             flat_registry[id(p)] = self.flat
         self.inv_scale = 1.0                   # amp: 1/S for the coming step
@@ -178,14 +200,32 @@ class FusedSGD(Optimizer):
         CUDA graph is being captured — the captured kernels read the table, whoever replays them calls this first)"""
         if self._lr_dev is None or torch.cuda.is_current_stream_capturing():
             return
-        n = 0
-        for g, (b, e) in zip(self.param_groups, self.flat.ranges):
-            if e > b:
-                lr = float(g["lr"])
-                if self._lr_sent[n] != lr:
-                    self._lr_dev[n].fill_(lr)
-                    self._lr_sent[n] = lr
-                n += 1
+        for n, (_, _, g, _) in enumerate(self._segment_plan()):
+            lr = float(g["lr"]) if g is not None else 0.0
+            if self._lr_sent[n] != lr:
+                self._lr_dev[n].fill_(lr)
+                self._lr_sent[n] = lr
+
+    def _bf16_exclusive(self) -> bool:
+        """True when the gradients of the convolution parameters exist in the bf16 buffer only: the shadow is installed and
+        autograd has not written into the fp32 flat buffer since the last step (it does when the model ran outside
+        autocast — then the kernels fall back to reading both buffers)"""
+        f = self.flat
+        return f.grad16 is not None and bool(f.shadow_leaves) and f.grad._version == self._clean_version[0]
+
+    def _segment_plan(self):
+        """[(begin, end, param_group | None for the frozen leftovers, bf16_only)] — the kernels' segment table; the layout
+        (not the flags) is fixed at construction, so the number of segments and their order never change"""
+        plan = []
+        buckets = list(zip([*self.param_groups, None], self.flat.ranges, self.flat.splits))
+        for g, (b, e), mid in buckets:
+            if e <= b:
+                continue
+            if self.flat.grad16 is not None and b < mid < e:
+                plan.append((b, mid, g, True)); plan.append((mid, e, g, False))
+            else:
+                plan.append((b, e, g, self.flat.grad16 is not None and mid == e))
+        return plan
 
     # -- torch.optim.Optimizer protocol -------------------------------------------------------------------
     def zero_grad(self, set_to_none: bool = False):
@@ -235,17 +275,16 @@ class FusedSGD(Optimizer):
             _lib.count_launch((len(items) + _lib.SOD_GATHER_MAX_ITEMS - 1) // _lib.SOD_GATHER_MAX_ITEMS)
 
     def _segments(self):
-        segs = (_lib.sod_sgd_segment * (len(self.param_groups) + 1))()
-        n = 0
-        for g, (b, e) in zip(self.param_groups, self.flat.ranges):
-            if e > b:
-                segs[n] = _lib.sod_sgd_segment(b, e, float(g["lr"]), float(g["weight_decay"]), float(g["momentum"]), 0)
-                n += 1
-        b, e = self.flat.ranges[-1]
-        if e > b:
-            segs[n] = _lib.sod_sgd_segment(b, e, 0.0, 0.0, 0.0, _lib.SOD_SEG_FROZEN)
-            n += 1
-        return segs, n
+        plan = self._segment_plan()
+        exclusive = self._bf16_exclusive()
+        segs = (_lib.sod_sgd_segment * max(len(plan), 1))()
+        for n, (b, e, g, bf16_part) in enumerate(plan):
+            flags = _lib.SOD_SEG_GRAD16 if (bf16_part and exclusive) else 0
+            if g is None:
+                segs[n] = _lib.sod_sgd_segment(b, e, 0.0, 0.0, 0.0, flags | _lib.SOD_SEG_FROZEN)
+            else:
+                segs[n] = _lib.sod_sgd_segment(b, e, float(g["lr"]), float(g["weight_decay"]), float(g["momentum"]), flags)
+        return segs, len(plan)
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -268,12 +307,15 @@ class FusedSGD(Optimizer):
             _lib.check(rc, "sod_sgd_momentum")
         else:
             a = f.arena
-            if g16 is not None:     # peers read the fp32 symmetric buffer: fold the local bf16 gradients in first
+            if g16 is not None and not self._bf16_exclusive():
+                # fp32 gradients were written for the convolution parameters too (model ran outside autocast): fold the
+                # bf16 ones into the fp32 symmetric buffer and exchange that
                 rc = _lib.lib().sod_grad_merge_bf16(f.grad.data_ptr(), g16, f.numel, _lib.stream_ptr())
                 _lib.check(rc, "sod_grad_merge_bf16")
                 _lib.count_launch()
-            rc = _lib.lib().sod_allreduce_sgd(a.ref, f.grad_off, f.param_off, f.mom.data_ptr(), s16, f.numel, segs, n,
-                                              lr_dev, float(self.inv_scale), finf, _lib.SOD_SGD_ZERO_GRAD, _lib.stream_ptr())
+            rc = _lib.lib().sod_allreduce_sgd(a.ref, f.grad_off, f.grad16_off if g16 is not None else 0, f.param_off,
+                                              f.mom.data_ptr(), s16, f.numel, segs, n, lr_dev, float(self.inv_scale), finf,
+                                              _lib.SOD_SGD_ZERO_GRAD, _lib.stream_ptr())
             _lib.check(rc, "sod_allreduce_sgd")
         _lib.count_launch()
         self._grads_clean = True

@@ -45,7 +45,7 @@ class DistributedDataParallel(nn.Module):
             self.flat = FlatParams([params], [])
             self._explicit_allreduce = True
         n = self.flat.numel
-        self.arena = comm.Arena(payload_bytes=2 * (4 * n + 256) + 1024, group=process_group)
+        self.arena = comm.Arena(payload_bytes=2 * (4 * n + 256) + (2 * n + 256) + 1024, group=process_group)   # p, g fp32 + g bf16
         p_off = self.arena.alloc(4 * n)
         g_off = self.arena.alloc(4 * n)
         self.flat.relocate(self.arena, p_off, g_off)

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SOD_ABI_VERSION 6
+#define SOD_ABI_VERSION 7
 #define SOD_MAX_WORLD 8
 #define SOD_MAX_SEGMENTS 16
 #define SOD_COMM_MAX_BLOCKS 1024   /* flag rows per channel */
@@ -107,7 +107,9 @@ size_t sod_comm_flag_bytes(void);
  * cast).  With world>1 the bf16 gradients are folded into the fp32 symmetric buffer by sod_grad_merge_bf16 first,
  * and `shadow16` is the LOCAL bf16 buffer every rank refreshes from the all-gathered parameters.
  * ------------------------------------------------------------------------------------------------ */
-enum { SOD_SEG_FROZEN = 1 };
+enum { SOD_SEG_FROZEN = 1,
+       SOD_SEG_GRAD16 = 2 /* the gradient of this range exists ONLY in the bf16 buffer (`grad16`): the fp32 buffer is neither read
+                             nor cleared there, and with world>1 the bf16 values themselves cross NVLink (summed in fp32) */ };
 typedef struct {
     int64_t begin, end;        /* element range, multiples of 4 */
     float lr, weight_decay, momentum;
@@ -131,9 +133,12 @@ enum { SOD_SGD_ZERO_GRAD = 1, SOD_ALGO_NO_MULTIMEM = 2,
 int sod_sgd_momentum(float* param, float* mom, float* grad, void* grad16, void* shadow16, int64_t n,
                      const sod_sgd_segment* segs, int nseg, const float* lr_dev, float inv_scale,
                      const uint32_t* found_inf, int flags, void* stream);
-int sod_allreduce_sgd(const sod_comm* comm, uint64_t grad_off, uint64_t param_off, float* mom, void* shadow16,
-                      int64_t n, const sod_sgd_segment* segs, int nseg, const float* lr_dev, float inv_scale,
-                      const uint32_t* found_inf, int flags, void* stream);
+/* grad16_off (world>1): arena offset of the symmetric bf16 gradient buffer, or 0.  Ranges flagged SOD_SEG_GRAD16 are reduced
+ * from it (peer loads of the bf16 values, fp32 sum in rank order — half the reduce-scatter bytes and no merge pre-pass);
+ * all other ranges from the fp32 buffer at grad_off as before. */
+int sod_allreduce_sgd(const sod_comm* comm, uint64_t grad_off, uint64_t grad16_off, uint64_t param_off, float* mom,
+                      void* shadow16, int64_t n, const sod_sgd_segment* segs, int nseg, const float* lr_dev,
+                      float inv_scale, const uint32_t* found_inf, int flags, void* stream);
 /* Multi-tensor gather of bf16 gradients into the flat bf16 gradient buffer (`grad16` above): item i copies
  * numel elements from the dense tensor `src` to dst16[dst_offset ...] (dst_offset % 8 == 0).  Replaces the
  * per-parameter accumulate kernels autograd launches at the end of backward (train.py:302): the weight gradients are

@@ -91,7 +91,7 @@ def _w_allreduce_sgd(rank, world):
         mom = torch.tensor(ve, device="cuda")
         p.copy_(torch.tensor(pe)); g.copy_(torch.tensor(grads[rank]))
         torch.cuda.synchronize(); torch.distributed.barrier()
-        rc = _lib.lib().sod_allreduce_sgd(arena.ref, g_off, p_off, mom.data_ptr(), None, n, segs, 3, None, 0.5, None, flags,
+        rc = _lib.lib().sod_allreduce_sgd(arena.ref, g_off, 0, p_off, mom.data_ptr(), None, n, segs, 3, None, 0.5, None, flags,
                                           torch.cuda.current_stream().cuda_stream)
         assert rc == 0
         torch.cuda.synchronize(); torch.distributed.barrier()
@@ -367,3 +367,51 @@ def _w_graph_step(rank, world):
 @needs2
 def test_graph_replay_world2_matches_eager():
     _spawn("_w_graph_step")
+
+
+def _w_allreduce_sgd_bf16_wire(rank, world):
+    """ABI v7: ranges flagged SOD_SEG_GRAD16 are reduced from the symmetric bf16 gradient buffer (the bf16 values cross
+    NVLink, fp32 sum in rank order), the rest from the fp32 buffer — against the oracle on the same (bf16-rounded) inputs"""
+    from oracle import sgd as osgd
+    from distributed_sod_project_b200 import _lib, comm
+    n = 1_000_000 + 64
+    arena = comm.Arena(payload_bytes=2 * 4 * n + 2 * n + 4096)
+    p_off, g_off, h_off = arena.alloc(4 * n), arena.alloc(4 * n), arena.alloc(2 * n)
+    rng = np.random.default_rng(5)
+    p0 = rng.standard_normal(n).astype(np.float32); v0 = rng.standard_normal(n).astype(np.float32)
+    a, b = (n // 3) // 4 * 4, (2 * n // 3) // 4 * 4
+    g32 = [np.random.default_rng(50 + r).standard_normal(n).astype(np.float32) for r in range(world)]
+    g16 = [torch.tensor(np.random.default_rng(90 + r).standard_normal(n).astype(np.float32)).to(torch.bfloat16) for r in range(world)]
+    # effective gradient per rank: bf16 buffer in [0, a), fp32 buffer in [a, b); [b, n) frozen
+    eff = [np.concatenate([g16[r][:a].float().numpy(), g32[r][a:]]) for r in range(world)]
+    segs_o = [osgd.Segment(0, a, 0.005, 5e-4, 0.9), osgd.Segment(a, b, 0.05, 5e-4, 0.9), osgd.Segment(b, n, 0, 0, frozen=True)]
+    segs = (_lib.sod_sgd_segment * 3)(_lib.sod_sgd_segment(0, a, 0.005, 5e-4, 0.9, _lib.SOD_SEG_GRAD16), _lib.sod_sgd_segment(a, b, 0.05, 5e-4, 0.9, 0),
+                                      _lib.sod_sgd_segment(b, n, 0, 0, 0, _lib.SOD_SEG_FROZEN))
+    for flags in (_lib.SOD_SGD_ZERO_GRAD, _lib.SOD_SGD_ZERO_GRAD | _lib.SOD_ALGO_NO_MULTIMEM):
+        p = arena.view(p_off, n, torch.float32); g = arena.view(g_off, n, torch.float32); h = arena.view(h_off, n, torch.bfloat16)
+        mom = torch.tensor(v0, device="cuda"); shadow = torch.zeros(n, dtype=torch.bfloat16, device="cuda")
+        p.copy_(torch.tensor(p0)); g.copy_(torch.tensor(g32[rank])); h.copy_(g16[rank])
+        g[:a].fill_(123.0)                                   # garbage in the fp32 buffer where the bf16 one rules
+        torch.cuda.synchronize(); torch.distributed.barrier()
+        rc = _lib.lib().sod_allreduce_sgd(arena.ref, g_off, h_off, p_off, mom.data_ptr(), shadow.data_ptr(), n, segs, 3, None, 1.0, None, flags,
+                                          torch.cuda.current_stream().cuda_stream)
+        assert rc == 0
+        torch.cuda.synchronize(); torch.distributed.barrier()
+        pe, ve = p0.copy(), v0.copy()
+        assert osgd.sgd_step(pe, ve, osgd.allreduce_mean(eff), segs_o, inv_scale=1.0)
+        np.testing.assert_allclose(p.cpu().numpy(), pe, rtol=3e-6, atol=1e-6)
+        shard = (n // 4 + world - 1) // world * 4
+        lo, hi = rank * shard, min(n, (rank + 1) * shard)
+        np.testing.assert_allclose(mom.cpu().numpy()[lo:hi], ve[lo:hi], rtol=3e-6, atol=1e-6)
+        assert float(g[a:].abs().max()) == 0.0 and float(g[:a].min()) == 123.0       # fp32 buffer: cleared only where it is in use
+        assert float(h.float().abs().max()) == 0.0
+        assert torch.equal(shadow, p.to(torch.bfloat16))
+        other = p.clone(); torch.distributed.broadcast(other, 0)
+        assert torch.equal(p, other)
+        torch.distributed.barrier()
+    arena.check_error()
+
+
+@needs2
+def test_allreduce_sgd_bf16_wire_vs_oracle():
+    _spawn("_w_allreduce_sgd_bf16_wire")

@@ -175,3 +175,29 @@ def test_multi_tensor_gather_of_bf16_gradients():
         off += pad
     bad = (_lib.sod_gather_item * 1)(_lib.sod_gather_item(srcs[0].data_ptr(), 4, 1))
     assert _lib.lib().sod_grad_gather16(bad, 1, flat.data_ptr(), flat_n, torch.cuda.current_stream().cuda_stream) == -2
+
+
+def test_bf16_only_gradient_segments():
+    """SOD_SEG_GRAD16 (ABI v7): in such a range the gradient is taken from the bf16 buffer alone — the fp32 buffer is neither
+    read (garbage there must not matter) nor cleared; other ranges keep adding both buffers."""
+    from distributed_sod_project_b200 import _lib
+    n = 4096 + 64
+    a = 2048
+    g = torch.Generator().manual_seed(9)
+    p0 = torch.randn(n, generator=g).cuda(); v0 = torch.randn(n, generator=g).cuda()
+    g32 = torch.randn(n, generator=g).cuda(); g16 = torch.randn(n, generator=g).to(torch.bfloat16).cuda()
+    p, v, gg, hh = p0.clone(), v0.clone(), g32.clone(), g16.clone()
+    shadow = torch.zeros(n, dtype=torch.bfloat16, device="cuda")
+    segs = (_lib.sod_sgd_segment * 2)(_lib.sod_sgd_segment(0, a, 0.1, 5e-4, 0.9, _lib.SOD_SEG_GRAD16), _lib.sod_sgd_segment(a, n, 0.01, 0.0, 0.9, 0))
+    rc = _lib.lib().sod_sgd_momentum(p.data_ptr(), v.data_ptr(), gg.data_ptr(), hh.data_ptr(), shadow.data_ptr(), n, segs, 2, None, 1.0, None,
+                                     _lib.SOD_SGD_ZERO_GRAD, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    eff = torch.cat([g16[:a].float(), g32[a:] + g16[a:].float()])
+    wd = torch.cat([torch.full((a,), 5e-4), torch.zeros(n - a)]).cuda(); lr = torch.cat([torch.full((a,), 0.1), torch.full((n - a,), 0.01)]).cuda()
+    ev = 0.9 * v0 + (eff + wd * p0)
+    ep = p0 - lr * ev
+    assert torch.allclose(v, ev, rtol=3e-6, atol=1e-6) and torch.allclose(p, ep, rtol=3e-6, atol=1e-6)
+    assert torch.equal(gg[:a], g32[:a]) and float(gg[a:].abs().max()) == 0.0          # fp32 buffer untouched in the bf16-only range
+    assert float(hh.float().abs().max()) == 0.0
+    assert torch.equal(shadow, p.to(torch.bfloat16))

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(h, name), f"{name} declared in include/sod_b200.h but not exported"
     assert declared == set(_lib.EXPORTS)
     lib = _lib.lib()
-    assert lib.sod_version() == 6
+    assert lib.sod_version() == 7
     assert lib.sod_comm_flag_bytes() == 4 * 1024 * 8 * 4
     assert lib.sod_syncbn_exchange_bytes(64) == 8 * 2 * 64 * 8
     assert b"workspace" in lib.sod_strerror(-3)

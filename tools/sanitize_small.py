@@ -52,7 +52,7 @@ if world > 1:
     arena.view(p_off, n, torch.float32).copy_(p); arena.view(g_off, n, torch.float32).copy_(g)
     torch.cuda.synchronize(); dist.barrier()
     for flags in (1, 1 | _lib.SOD_ALGO_NO_MULTIMEM):
-        assert _lib.lib().sod_allreduce_sgd(arena.ref, g_off, p_off, v.data_ptr(), None, n, segs, 1, None, 1.0, None, flags, _lib.stream_ptr()) == 0
+        assert _lib.lib().sod_allreduce_sgd(arena.ref, g_off, 0, p_off, v.data_ptr(), None, n, segs, 1, None, 1.0, None, flags, _lib.stream_ptr()) == 0
     arena.allreduce_(g_off, n, algo=1); arena.allreduce_(g_off, n, algo=2)
     torch.cuda.synchronize(); dist.barrier()
     arena.check_error(); comm.small_arena().check_error()
