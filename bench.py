@@ -169,17 +169,72 @@ def pick_threads(factory) -> int:
     return best
 
 
+def _cpu_world_worker(rank, world, port, model_name, batch, steps, warmup, threads, out_path):
+    """one CPU rank of the reference's DDP + SyncBN loop over gloo (oracle/step.py restatement)"""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.set_num_threads(threads)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle.step import OracleTrainer
+    from distributed_sod_project_b200 import network
+    from distributed_sod_project_b200.synthetic import synth_batch
+    tr = OracleTrainer(getattr(network, model_name), world_size=world, seed=0)
+    batches = [synth_batch(1234 + rank + 100 * i, batch, SIZE) for i in range(2)]
+    for i in range(warmup):
+        tr.step(*batches[i % 2])
+    dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        tr.step(*batches[i % 2])
+    dist.barrier()
+    dt = (time.perf_counter() - t0) / steps
+    if rank == 0:
+        json.dump({"dt": dt}, open(out_path, "w"))
+    dist.destroy_process_group()
+
+
+def cpu_reference_world(model_name: str, world: int, batch: int, steps: int, warmup: int):
+    """the reference's distributed loop (apex DDP + SyncBN semantics restated over gloo) with
+    `world` CPU ranks on this host, the available cores split between them"""
+    import socket
+    import tempfile
+    import torch.multiprocessing as mp
+    from distributed_sod_project_b200 import network
+    cores = pick_threads(getattr(network, model_name))
+    threads = max(1, cores // world)
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    out = os.path.join(tempfile.mkdtemp(), "cpu_world.json")
+    mp.spawn(_cpu_world_worker, args=(world, port, model_name, batch, steps, warmup, threads, out), nprocs=world, join=True)
+    dt = json.load(open(out))["dt"]
+    return {"value": world * batch / dt, "unit": UNIT, "cores": threads * world, "kind": "port",
+            "sample": f"{steps} steps of bs={batch}/rank x {world} gloo ranks at {SIZE}x{SIZE} fp32 ({model_name}, oracle/step.py: "
+                      f"reference train.py:284-310 with apex DDP + SyncBN semantics over gloo, {threads} torch threads per rank)",
+            "ms_per_step": dt * 1e3}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     steps = max(1, args.steps)
-    res = cpu_reference(args.model, args.cpu_batch, steps, max(1, min(args.warmup, 3)))
+    warm = max(1, min(args.warmup, 3))
+    world = max(1, args.gpus)
+    if world > 1:
+        # the reference's distributed configuration on the host CPU: one gloo rank per GPU of the arm it is compared with;
+        # per-rank batch shrinks with the world so that a step stays a bounded sample (bs 4, 2, 1, 1 at 1, 2, 4, 8 ranks)
+        batch = max(1, args.cpu_batch // world)
+        steps = min(steps, 10)
+        res = cpu_reference_world(args.model, world, batch, steps, min(warm, 2))
+    else:
+        batch = args.cpu_batch
+        res = cpu_reference(args.model, batch, steps, warm)
     line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": max(1, min(args.warmup, 3)), "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "warmup": warm, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": f"TestModel {args.model} {SIZE}x{SIZE}, one training iteration (fwd+BCE/CEL+bwd+SGD), "
-                                   f"CPU sample bs={args.cpu_batch}"},
+            "config": {"workload": f"TestModel {args.model} {SIZE}x{SIZE}, one training iteration (fwd+BCE/CEL+bwd+SGD"
+                                   + (f", DDP + SyncBN over gloo, {world} CPU ranks" if world > 1 else "") + "), "
+                                   f"CPU sample bs={batch}" + ("/rank" if world > 1 else "")},
             "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)

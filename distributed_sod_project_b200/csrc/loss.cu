@@ -12,8 +12,9 @@
 //     every CTA re-reduces the ≤148 partials in the same fixed order (deterministic, no atomics);
 //   * phase 2 re-reads the slice FROM SHARED MEMORY and writes the gradient: logits and mask cross
 //     HBM exactly once (8 B/elem algorithmic with bf16 logits + fp32 mask + bf16 grad).
-// Slices larger than the shared-memory window (≈32 K elements per CTA, 4.8 M per launch) spill to a
-// streaming path that re-reads the overflow from global memory (L2) in phase 2.
+// Slices larger than the shared-memory window (≈36 K elements per CTA, 5.4 M per launch) take loss_stream_kernel
+// below: the slice flows through a shared-memory ring fed by a producer warp, and phase 2 re-streams what did not stay
+// resident (newest first, L2 eviction hints).
 #include "common.cuh"
 
 namespace sod {
@@ -197,6 +198,170 @@ __global__ void __launch_bounds__(kThreads, 1) loss_bce_cel_kernel(const LossPar
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// streaming variant for tensors larger than the resident window (SURVEY §8d's scaled shape [64,1,1024,1024]):
+// the slice flows through a shared-memory ring fed by a dedicated producer warp (same scheme as csrc/syncbn.cu):
+// phase 1 consumes every chunk once, the last `nstage` chunks stay resident; after the grid barrier phase 2 takes the
+// resident chunks first and re-streams the rest newest-first (the likeliest L2 hits), with L2 eviction hints:
+// evict-last for chunks that will be fetched again, evict-first for every last use.
+// ------------------------------------------------------------------------------------------------
+constexpr int kStreamBlock = kThreads + 32;
+constexpr int kMaxStreamStages = 12;
+
+struct StreamRing {
+    uint64_t* full;
+    uint64_t* empty;
+    uint32_t full_par, empty_par;
+    __device__ __forceinline__ void wait_full(int s) { mbar_wait(&full[s], (full_par >> s) & 1u); full_par ^= 1u << s; }
+    __device__ __forceinline__ void wait_empty(int s) { mbar_wait(&empty[s], (empty_par >> s) & 1u); empty_par ^= 1u << s; }
+    __device__ __forceinline__ void release(int s) {
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[s])) : "memory");
+    }
+};
+
+template <typename TX, typename TM>
+__global__ void __launch_bounds__(kStreamBlock, 1) loss_stream_kernel(const LossParams prm) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);          // full[12] | empty[12] (256 B reserved)
+    const int NS = prm.resident;                                     // stages of the ring
+    constexpr size_t kStage = static_cast<size_t>(kChunk) * (sizeof(TX) + sizeof(TM));
+    unsigned char* stages = smem_raw + 256;
+    __shared__ float s_red[kThreads / 32][4];
+    __shared__ double s_tot[4];
+
+    const TX* __restrict__ gx = static_cast<const TX*>(prm.x);
+    const TM* __restrict__ gm = static_cast<const TM*>(prm.m);
+    TX* __restrict__ gg = static_cast<TX*>(prm.g);
+    const int tid = threadIdx.x;
+    const long long n = prm.n;
+    const long long nvec = n & ~7ll;
+    long long e0 = static_cast<long long>(blockIdx.x) * prm.per_cta;
+    long long e1 = e0 + prm.per_cta;
+    if (e0 > nvec) e0 = nvec;
+    if (e1 > nvec) e1 = nvec;
+    const int nchunks = static_cast<int>((e1 - e0 + kChunk - 1) / kChunk);
+    const int nres0 = nchunks > NS ? nchunks - NS : 0;               // chunks [nres0, nchunks) stay resident after phase 1
+    const int total_loads = nchunks + nres0;
+
+    StreamRing ring{bars, bars + kMaxStreamStages, 0u, 0u};
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) { mbar_init(&ring.full[s], 1); mbar_init(&ring.empty[s], kThreads / 32); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto sx_of = [&](int s) { return reinterpret_cast<TX*>(stages + static_cast<size_t>(s) * kStage); };
+    auto sm_of = [&](int s) { return reinterpret_cast<TM*>(stages + static_cast<size_t>(s) * kStage + static_cast<size_t>(kChunk) * sizeof(TX)); };
+    auto cnt_of = [&](int c) -> int {
+        const long long base = e0 + static_cast<long long>(c) * kChunk;
+        return static_cast<int>((e1 - base) < kChunk ? (e1 - base) : kChunk);
+    };
+
+    if (tid >= kThreads) {   // ---- producer warp --------------------------------------------------------------------
+        if ((tid & 31) == 0) {
+            for (int k = 0; k < total_loads; ++k) {
+                if (k == nchunks) cg::this_grid().sync();            // phase-1 loads are all issued: join the grid barrier
+                const int s = k % NS;
+                if (k >= NS) ring.wait_empty(s);
+                const int c = k < nchunks ? k : nres0 - 1 - (k - nchunks);
+                const long long base = e0 + static_cast<long long>(c) * kChunk;
+                const uint32_t cnt = static_cast<uint32_t>(cnt_of(c));
+                const uint64_t policy = (k < nchunks && k < nres0) ? kL2EvictLast : kL2EvictFirst;
+                mbar_arrive_expect_tx(&ring.full[s], cnt * static_cast<uint32_t>(sizeof(TX) + sizeof(TM)));
+                bulk_g2s_hint(sx_of(s), gx + base, cnt * static_cast<uint32_t>(sizeof(TX)), &ring.full[s], policy);
+                bulk_g2s_hint(sm_of(s), gm + base, cnt * static_cast<uint32_t>(sizeof(TM)), &ring.full[s], policy);
+            }
+            if (total_loads <= nchunks) cg::this_grid().sync();      // nothing to re-stream: the barrier was not met inside the loop
+        } else {
+            cg::this_grid().sync();
+        }
+        return;
+    }
+
+    // ---- phase 1 ---------------------------------------------------------------------------------------------------
+    Sums acc{0.f, 0.f, 0.f, 0.f};
+    for (int i = 0; i < nchunks; ++i) {
+        const int s = i % NS;
+        ring.wait_full(s);
+        const int cnt = cnt_of(i);
+        const int e = tid * 8;
+        if (e < cnt) {
+            float xv[8], tv[8];
+            IO<TX>::load8(sx_of(s) + e, xv);
+            IO<TM>::load8(sm_of(s) + e, tv);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) loss_terms(xv[k], tv[k], acc);
+        }
+        if (i + NS < nchunks) ring.release(s);
+    }
+    const int ntail = static_cast<int>(n - nvec);
+    if (blockIdx.x == 0 && tid < ntail)
+        loss_terms(IO<TX>::load1(gx + nvec + tid), IO<TM>::load1(gm + nvec + tid), acc);
+    {
+        const float a = warp_sum(acc.bce), b = warp_sum(acc.p), c2 = warp_sum(acc.t), d = warp_sum(acc.pt);
+        if ((tid & 31) == 0) { s_red[tid >> 5][0] = a; s_red[tid >> 5][1] = b; s_red[tid >> 5][2] = c2; s_red[tid >> 5][3] = d; }
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (tid == 0) {
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int w = 0; w < kThreads / 32; ++w) { o.x += s_red[w][0]; o.y += s_red[w][1]; o.z += s_red[w][2]; o.w += s_red[w][3]; }
+            prm.partials[blockIdx.x] = o;
+        }
+    }
+    cg::this_grid().sync();
+    if (tid < 32) {
+        double a = 0, b = 0, c2 = 0, d = 0;
+        for (int i = tid; i < static_cast<int>(gridDim.x); i += 32) {
+            const float4 v = prm.partials[i];
+            a += v.x; b += v.y; c2 += v.z; d += v.w;
+        }
+        a = warp_sum(a); b = warp_sum(b); c2 = warp_sum(c2); d = warp_sum(d);
+        if (tid == 0) { s_tot[0] = a; s_tot[1] = b; s_tot[2] = c2; s_tot[3] = d; }
+    }
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    const double bce_sum = s_tot[0], sp = s_tot[1], st = s_tot[2], spt = s_tot[3];
+    const double num = sp + st - 2.0 * spt;
+    const double den = sp + st + static_cast<double>(prm.eps);
+    const double cel = num / den;
+    const double bce = prm.reduction_sum ? bce_sum : bce_sum / static_cast<double>(n);
+    if (blockIdx.x == 0 && tid == 0) {
+        float* o = prm.scalars;
+        o[0] = static_cast<float>(bce); o[1] = static_cast<float>(cel);
+        o[2] = static_cast<float>(prm.w_bce * bce + prm.w_cel * cel);
+        o[3] = static_cast<float>(sp); o[4] = static_cast<float>(st); o[5] = static_cast<float>(spt);
+        o[6] = static_cast<float>(bce_sum); o[7] = static_cast<float>(n);
+    }
+    const float kb = prm.grad_scale * prm.w_bce * (prm.reduction_sum ? 1.0f : static_cast<float>(1.0 / static_cast<double>(n)));
+    const float alpha = static_cast<float>(static_cast<double>(prm.grad_scale) * prm.w_cel / den);
+    const float beta = static_cast<float>(-static_cast<double>(prm.grad_scale) * prm.w_cel * num / (den * den));
+
+    // ---- phase 2: resident chunks first, then the re-streamed ones (newest first) ----------------------------------
+    const int nresident = nchunks - nres0;
+    for (int u = 0; u < nchunks; ++u) {
+        const bool streamed = u >= nresident;
+        const int c = streamed ? nres0 - 1 - (u - nresident) : nres0 + u;
+        const int kload = nchunks + (u - nresident);
+        const int s = streamed ? kload % NS : (nres0 + u) % NS;
+        if (streamed) ring.wait_full(s);
+        const long long base = e0 + static_cast<long long>(c) * kChunk;
+        const int cnt = cnt_of(c);
+        const int e = tid * 8;
+        if (e < cnt) {
+            float xv[8], tv[8], gv[8];
+            IO<TX>::load8(sx_of(s) + e, xv);
+            IO<TM>::load8(sm_of(s) + e, tv);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) gv[k] = loss_grad(xv[k], tv[k], kb, alpha, beta);
+            IO<TX>::store8(gg + base + e, gv);
+        }
+        const int stage_load = streamed ? kload : nres0 + u;
+        if (stage_load + NS < total_loads) ring.release(s);
+    }
+    if (blockIdx.x == 0 && tid < ntail) {
+        const float x = IO<TX>::load1(gx + nvec + tid), t = IO<TM>::load1(gm + nvec + tid);
+        IO<TX>::store1(gg + nvec + tid, loss_grad(x, t, kb, alpha, beta));
+    }
+}
+
 template <typename T>
 __global__ void scale_by_scalar_kernel(T* g, long long n, const float* s) {
     const float sc = *s;
@@ -235,6 +400,21 @@ int launch_loss(LossParams& prm, int mode, cudaStream_t stream) {
     if (mode == 1 && need > resident) return SOD_EUNSUPPORTED;  // caller demanded the single-read path
 
     prm.per_cta = per_cta;
+    if (need > resident) {
+        // larger than the resident window: the ring-streamed kernel (mode 2 = "streaming" selects it as well)
+        auto skern = loss_stream_kernel<TX, TM>;
+        int stages = static_cast<int>((static_cast<size_t>(dv.max_smem_optin) - 256 - 1024) / per_chunk);
+        if (stages > kMaxStreamStages) stages = kMaxStreamStages;
+        if (stages < 2) return SOD_EUNSUPPORTED;
+        prm.resident = stages;
+        const size_t ssmem = 256 + static_cast<size_t>(stages) * per_chunk;
+        cudaError_t e = cudaFuncSetAttribute(skern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ssmem));
+        if (e != cudaSuccess) return static_cast<int>(e);
+        void* sargs[] = {&prm};
+        e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(skern), dim3(static_cast<unsigned>(grid)), dim3(kStreamBlock), sargs,
+                                        ssmem, stream);
+        return static_cast<int>(e);
+    }
     prm.resident = resident;
     const size_t smem = 128 + static_cast<size_t>(resident) * per_chunk;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));

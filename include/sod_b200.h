@@ -52,7 +52,9 @@ int sod_device_info(int* sm_count, int* cc_major, int* cc_minor);
  *           get_total_loss (utils/pipeline_ops.py:37-42), and their autograd backward (train.py:302).
  *   total = w_bce*BCE(reduction) + w_cel*CEL;  grad = grad_scale * d total / d logits
  * scalars_out[8] (device, fp32): bce, cel, total, sum_p, sum_t, sum_pt, bce_sum(unreduced), n
- * mode: 0 auto, 1 force the shared-memory-resident single-read path, 2 force the streaming two-pass path
+ * mode: 0 auto (resident when the tensor fits the grid's shared memory, ≈5.4 M elements, else ring-streamed), 1 force the
+ *       shared-memory-resident single-read kernel, 2 force the ring-streamed kernel (producer warp + shared-memory ring;
+ *       phase 2 re-streams what did not stay resident, newest first, with L2 eviction hints)
  * workspace: sod_loss_workspace_bytes() bytes, 16-byte aligned; contents need not be initialised.
  * ------------------------------------------------------------------------------------------------ */
 size_t sod_loss_workspace_bytes(void);

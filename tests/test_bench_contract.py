@@ -27,3 +27,14 @@ def test_reference_arm_only_rank0_prints():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"],
                          capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_reference_arm_world2_is_the_gloo_ddp_syncbn_loop():
+    """at N > 1 the reference arm times the reference's DISTRIBUTED loop on the host: N gloo ranks"""
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1",
+                          "--cpu-batch", "2"], capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][0])
+    assert d["n_gpus"] == 2 and "2 gloo ranks" in d["cpu_baseline"]["sample"] and "2 CPU ranks" in d["config"]["workload"]
+    assert d["value"] > 0 and d["e2e"]["value"] == d["value"]

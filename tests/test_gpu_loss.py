@@ -126,3 +126,24 @@ def test_rejects_cpu_and_misuse():
         bce_cel_fwd_bwd(torch.zeros(4), torch.zeros(4))
     with pytest.raises(ValueError):
         bce_cel_fwd_bwd(torch.zeros(4, device="cuda"), torch.zeros(5, device="cuda"))
+
+
+@pytest.mark.parametrize("n", [4096 * 3 + 5, 148 * 4096 * 9, 148 * 4096 * 10 + 777, 148 * 4096 * 23 + 8, 33_000_001])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_ring_streamed_kernel_matches_oracle(n, dtype):
+    """mode 2 forces the ring-streamed kernel (producer warp + shared-memory ring, re-stream newest first): fewer chunks
+    than stages (nothing re-streamed), exactly as many, one more, many more, and a ragged scalar tail"""
+    from distributed_sod_project_b200.loss import bce_cel_fwd_bwd
+    gcpu = torch.Generator().manual_seed(n % 1000)
+    x = (torch.randn(n, generator=gcpu) * 3).to(dtype)
+    t = (torch.rand(n, generator=gcpu) > 0.6).float()
+    ref = oloss.bce_cel_fwd_bwd(x.float().numpy(), t.numpy())
+    scalars, grad = bce_cel_fwd_bwd(x.cuda(), t.cuda(), mode=2)
+    s = scalars.cpu().numpy()
+    assert s[0] == pytest.approx(ref["bce"], rel=2e-5) and s[1] == pytest.approx(ref["cel"], rel=2e-5)
+    gr = grad.float().cpu().numpy().astype(np.float64)
+    scale = np.abs(ref["grad"]).max()
+    tol = 1e-5 if dtype == torch.float32 else 1.5 * 2.0 ** -8
+    assert np.abs(gr - ref["grad"]).max() / scale < tol
+    resident, _ = bce_cel_fwd_bwd(x.cuda(), t.cuda(), mode=0)
+    assert resident.cpu().numpy()[2] == pytest.approx(s[2], rel=1e-6)
