@@ -440,7 +440,8 @@ def parity_check(tr, rank: int, world: int) -> dict:
                     eff[b:e] = grad[b:e]
             assert opt._bf16_exclusive()
         else:
-            flat.grad.copy_(grad)                                      # fp32 everywhere (bumps the version: fp32 wire format)
+            flat.grad.copy_(grad)                                      # fp32 everywhere ...
+            flat.master_grads_seen = True                              # ... which is what a run outside autocast leaves: fp32 wire format
             if flat.grad16 is not None:
                 flat.grad16.zero_()
             eff = grad

@@ -69,6 +69,15 @@ def _install_shadow_weights(model, flat) -> int:
 
         m.forward = forward
         count += 1
+    def _seen(grad, flat=flat):
+        flat.master_grads_seen = True          # a gradient reached an fp32 master: the bf16 buffer is no longer the whole story
+        return grad
+
+    for m in model.modules():
+        if isinstance(m, nn.Conv2d) and hasattr(m, "_sod_w16"):
+            for p in (m.weight, m.bias):
+                if p is not None and id(p) in managed and p.requires_grad:
+                    p.register_hook(_seen)
     model.register_load_state_dict_post_hook(lambda mod, incompatible: flat.refresh_shadow())
     return count
 

@@ -33,7 +33,7 @@ def rank() -> int:
 
 
 class Arena:
-    def __init__(self, payload_bytes: int, group=None, device: torch.device | None = None, timeout_s: float = 10.0):
+    def __init__(self, payload_bytes: int, group=None, device: torch.device | None = None, timeout_s: float = 30.0):
         if not dist_ready():
             raise _lib.SodError("Arena needs an initialised torch.distributed process group")
         import torch.distributed._symmetric_memory as symm

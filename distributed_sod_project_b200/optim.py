@@ -73,6 +73,9 @@ class FlatParams:
         # steal=True: `.grad` is left None so that autograd hands over cuDNN's gradient tensor as it is (no accumulate
         # kernel per parameter); FusedSGD.step collects all of them into `grad16` with one sod_grad_gather16 launch
         self.shadow_leaves: list[tuple[torch.Tensor, int, bool]] = []
+        # set by a hook on the fp32 masters of shadowed parameters (amp._install_shadow_weights) when a gradient reaches one
+        # of them — the model ran outside autocast — and cleared by the step that has consumed it
+        self.master_grads_seen = False
         self._bind(copy_from_params=True)
 
     # -- mixed precision: bf16 shadow of the fp32 master ---------------------------------------------------
@@ -208,10 +211,11 @@ class FusedSGD(Optimizer):
 
     def _bf16_exclusive(self) -> bool:
         """True when the gradients of the convolution parameters exist in the bf16 buffer only: the shadow is installed and
-        autograd has not written into the fp32 flat buffer since the last step (it does when the model ran outside
-        autocast — then the kernels fall back to reading both buffers)"""
+        no gradient has reached an fp32 master since the last step (one does when the model ran outside autocast — then the
+        kernels fall back to reading both buffers).  (Version counters cannot tell: at world > 1 the flat buffers are views
+        of ONE symmetric allocation and share its counter.)"""
         f = self.flat
-        return f.grad16 is not None and bool(f.shadow_leaves) and f.grad._version == self._clean_version[0]
+        return f.grad16 is not None and bool(f.shadow_leaves) and not f.master_grads_seen
 
     def _segment_plan(self):
         """[(begin, end, param_group | None for the frozen leftovers, bf16_only)] — the kernels' segment table; the layout
@@ -318,6 +322,7 @@ class FusedSGD(Optimizer):
                                               _lib.SOD_SGD_ZERO_GRAD, _lib.stream_ptr())
             _lib.check(rc, "sod_allreduce_sgd")
         _lib.count_launch()
+        f.master_grads_seen = False
         self._grads_clean = True
         self._clean_version = self._grad_versions()
         self._stepped = True
