@@ -171,9 +171,13 @@ def pick_threads(factory) -> int:
 
 def _cpu_world_worker(rank, world, port, model_name, batch, steps, warmup, threads, out_path):
     """one CPU rank of the reference's DDP + SyncBN loop over gloo (oracle/step.py restatement)"""
+    # under torchrun the parent's environment says "use the elastic agent's store" (TORCHELASTIC_USE_AGENT_STORE) and carries
+    # the NCCL job's rank variables: this CPU job is a separate group with a TCP store of its own
+    for k in [k for k in os.environ if k.startswith(("TORCHELASTIC_", "GROUP_", "ROLE_", "LOCAL_WORLD", "TORCH_NCCL"))]:
+        os.environ.pop(k, None)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     torch.set_num_threads(threads)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     from oracle.step import OracleTrainer
     from distributed_sod_project_b200 import network
     from distributed_sod_project_b200.synthetic import synth_batch

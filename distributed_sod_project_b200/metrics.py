@@ -185,7 +185,9 @@ class SaliencyMetrics:
         vec = np.concatenate([[self._count], [self._sums[k] for k in ("mae", "meanf", "sm", "em", "wfm")], self._precision, self._recall])
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
-            t = torch.tensor(vec, dtype=torch.float64, device="cuda")
+            # NCCL reduces device tensors; a gloo group (CPU tests of this host logic) reduces host tensors
+            dev = "cuda" if dist.get_backend(self.group) == "nccl" else "cpu"
+            t = torch.tensor(vec, dtype=torch.float64, device=dev)
             dist.all_reduce(t, group=self.group)
             vec = t.cpu().numpy()
         num = vec[0]
