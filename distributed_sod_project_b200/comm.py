@@ -132,5 +132,5 @@ def allreduce_tensor(tensor: torch.Tensor) -> torch.Tensor:
     stage = a.view(a.scalar_off, pad, torch.float32)
     stage.zero_()
     stage[:n].copy_(tensor.detach().reshape(-1).float())
-    a.allreduce_(a.scalar_off, pad, scale=1.0 / a.world, algo=1)
+    a.allreduce_(a.scalar_off, pad, scale=1.0 / a.world, algo=0)     # auto: two-shot over NVLS when there is a multicast mapping
     return stage[:n].clone().view_as(tensor)

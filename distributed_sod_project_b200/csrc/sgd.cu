@@ -525,16 +525,19 @@ extern "C" int sod_allreduce_f32(const sod_comm* comm, uint64_t off, int64_t n, 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const long long one_shot_cap = static_cast<long long>(kThreads) * kUnroll *
                                    (dev_info().sm_count < SOD_COMM_MAX_BLOCKS ? dev_info().sm_count : SOD_COMM_MAX_BLOCKS);
-    if (algo == 0) algo = (n * 4 <= (256 << 10)) ? 1 : 2;
+    // measured (profiles/r02_call3_w2_sweep_w2.txt, extras.allreduce_sweep of the 4/8-GPU lines): the two-shot kernel over the
+    // NVLS mapping beats the one-shot kernel at every size once a multicast mapping exists (64 KB: 17-20 µs vs 24-43 µs);
+    // one-shot (every rank reads every peer) is only kept for fabrics without multicast
+    const bool has_mc = (c.mc != 0) && !(flags & SOD_ALGO_NO_MULTIMEM);
+    if (algo == 0) algo = (!has_mc && n * 4 <= (256 << 10)) ? 1 : 2;
     if (algo == 1 && nvec > one_shot_cap) return SOD_EUNSUPPORTED;
     if (algo == 1) {
         const unsigned grid = comm_grid(nvec);
         allreduce_one_shot_kernel<<<grid, kThreads, 0, s>>>(c, off, nvec, scale);
     } else {
         const unsigned grid = comm_grid((nvec + c.world - 1) / c.world);
-        // measured (profiles/r01_allreduce_sweep_w2.json): with two ranks the in-switch reduction loses to plain peer loads
-    // (288 vs 175 µs at 99.6 MB); from four ranks up NVLS wins (281 vs 346 µs at eight)
-    const bool mc = (c.mc != 0) && !(flags & SOD_ALGO_NO_MULTIMEM) && (c.world > 2 || (flags & SOD_ALGO_FORCE_MULTIMEM));
+        // in-switch reduction: always from four ranks up; with two ranks peer loads win above ≈2 MB (99.6 MB: 176 vs 288 µs)
+        const bool mc = has_mc && (c.world > 2 || n * 4 <= (2 << 20) || (flags & SOD_ALGO_FORCE_MULTIMEM));
         if (mc) allreduce_two_shot_kernel<true><<<grid, kThreads, 0, s>>>(c, off, nvec, scale);
         else allreduce_two_shot_kernel<false><<<grid, kThreads, 0, s>>>(c, off, nvec, scale);
     }

@@ -106,8 +106,10 @@ size_t sod_comm_flag_bytes(void);
  * the gradients autograd produced in bf16 — the kernel adds them to `grad` in registers, so no bf16→fp32 cast
  * kernel and no fp32 accumulation kernel run per tensor; `shadow16` (bf16, may be NULL) receives the rounded copy
  * of every updated parameter, which the next forward's convolutions consume directly (no per-iteration weight
- * cast).  With world>1 the bf16 gradients are folded into the fp32 symmetric buffer by sod_grad_merge_bf16 first,
- * and `shadow16` is the LOCAL bf16 buffer every rank refreshes from the all-gathered parameters.
+ * cast).  Ranges flagged SOD_SEG_GRAD16 take their gradient from `grad16` alone.  With world>1 `grad16` lives in the
+ * arena too (grad16_off) and those ranges are reduced from the bf16 values themselves; sod_grad_merge_bf16 is only needed
+ * when fp32 gradients were ALSO written for such a range (a forward outside autocast).  `shadow16` is the LOCAL bf16
+ * buffer every rank refreshes from the all-gathered parameters.
  * ------------------------------------------------------------------------------------------------ */
 enum { SOD_SEG_FROZEN = 1,
        SOD_SEG_GRAD16 = 2 /* the gradient of this range exists ONLY in the bf16 buffer (`grad16`): the fp32 buffer is neither read

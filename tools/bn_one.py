@@ -18,6 +18,6 @@ with torch.no_grad():
     weight = bn.weight.detach(); mean = torch.zeros(c, device="cuda"); invstd = torch.ones(c, device="cuda")
     for _ in range(3):
         flush.zero_()
-        raw_backward(dy, x, pre, y if relu else None, weight, mean, invstd, relu, has_res)
+        raw_backward(dy, x, pre, y if relu else None, weight, mean, invstd, relu, has_res, bias=bn.bias.detach())   # default variant: mask from x
 torch.cuda.synchronize()
 print("done")
