@@ -1,15 +1,15 @@
 #!/bin/bash
 # Static evidence for the shipped kernels (no GPU needed): ptxas resource usage per kernel and the SASS mnemonics that
 # show which hardware paths the code takes (UBLKCP = 1-D bulk async copy / TMA engine, SYNCS = mbarrier,
-# LDGMC / multimem = NVLS multicast loads).  Output: profiles/r01_static_report.txt
+# LDGMC / multimem = NVLS multicast loads).  Output: profiles/r02_static_report.txt
 set -e
 cd "$(dirname "$0")/.."
-OUT=profiles/r01_static_report.txt
+OUT=profiles/${SOD_ROUND:-r02}_static_report.txt
 LIB=distributed_sod_project_b200/libsod_b200.so
 TMP=$(mktemp -d)
 {
   echo "# ptxas -v (registers / spills / smem per kernel), nvcc $(nvcc --version | grep -o 'V[0-9]*\.[0-9]*\.[0-9]*')"
-  for f in loss sgd syncbn resample api; do
+  for f in loss sgd syncbn resample maxpool pipeline api; do
     nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Iinclude -Xptxas=-v \
          -c distributed_sod_project_b200/csrc/$f.cu -o $TMP/$f.o 2>&1 \
       | c++filt | awk '/Compiling entry function/ {name=$0; sub(/.*function ./,"",name); sub(/. for.*/,"",name)}
