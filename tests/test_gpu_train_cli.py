@@ -45,3 +45,13 @@ def test_train_cli_test_mode_evaluates_a_saved_checkpoint():
     assert out.count("Results on the valset(") == 1 and "Results on the testset(" not in out
     out = _run(1, dict(common, resume_mode="test"), 29704)
     assert "Loaded checkpoint" in out and out.count("Results on the testset(") == 6 and "[I:" not in out
+    # the reference's stand-alone evaluation script (test.py) on the same checkpoint: same numbers as train.py's test mode
+    env = dict(os.environ, SOD_CONFIG_JSON=json.dumps(dict(common, resume_mode="test")))
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "test.py")], cwd=ROOT, env=env, capture_output=True, text=True, timeout=500)
+    assert res.returncode == 0, res.stderr[-3000:]
+    import ast
+    mine = [ast.literal_eval(l) for l in res.stdout.splitlines() if l.startswith("{'MaxF'")]
+    theirs = [ast.literal_eval(l) for l in out.splitlines() if l.startswith("{'MaxF'")]
+    assert len(mine) == 6 == len(theirs)
+    for a, b in zip(mine, theirs):      # test.py runs the network in fp32 (as the reference's does), train.py's test mode under bf16 autocast
+        assert all(abs(a[k] - b[k]) < 3e-2 for k in ("MaxF", "MeanF", "MAE", "SM", "EM")), (a, b)
