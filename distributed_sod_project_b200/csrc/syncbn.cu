@@ -652,6 +652,18 @@ __global__ void __launch_bounds__(kBlock, 1) syncbn_fwd_kernel(const __grid_cons
         s_scale[ch] = prm.gamma[ch];
         s_shift[ch] = prm.beta[ch];
     }
+    // folded conv bias of this thread's first channel (every channel when C ≤ 512), also fetched ahead of the exchange
+    const float cb_first = (tid < C) ? ld_bias(prm.cbias1, prm.cbias_dtype, tid) + ld_bias(prm.cbias2, prm.cbias_dtype, tid) : 0.f;
+    // The per-channel global side effects (saved statistics, running statistics) are spread over the grid: channel ch
+    // belongs to CTA ch % gridDim — CTA 0 doing all C read-modify-writes after the exchange made it the last CTA to finish
+    // (≈1.8 µs behind the median, tools/bn_phases.py).  The old running values of the first owned channel are fetched now.
+    const int G = static_cast<int>(gridDim.x);
+    const int ch_own = static_cast<int>(blockIdx.x) + tid * G;
+    float rm_own = 0.f, rv_own = 0.f;
+    if (training && prm.rmean != nullptr && ch_own < C) {
+        rm_own = prm.rmean[ch_own];
+        rv_own = prm.rvar[ch_own];
+    }
 
     if (training) {
         // ---- phase 1: Σ(r − s), Σ(r − s)² from shared memory, r = x (+ pre) --------------------------------
@@ -725,27 +737,34 @@ __global__ void __launch_bounds__(kBlock, 1) syncbn_fwd_kernel(const __grid_cons
         const float n = static_cast<float>(g.rows) * static_cast<float>(prm.c.world);
         for (int ch = tid; ch < C; ch += kThreads) {
             const int ll = ch >> 3, k = ch & 7;
-            const float cbv = ld_bias(prm.cbias1, prm.cbias_dtype, ch) + ld_bias(prm.cbias2, prm.cbias_dtype, ch);
+            const float cbv = (ch == tid) ? cb_first : ld_bias(prm.cbias1, prm.cbias_dtype, ch) + ld_bias(prm.cbias2, prm.cbias_dtype, ch);
             const float mean = red[k * L + ll] + cbv;
             const float var = red[(8 + k) * L + ll];
             const float invstd = 1.0f / sqrtf(var + prm.eps);
             const float sc = invstd * s_scale[ch];
             s_scale[ch] = sc;
             s_shift[ch] = fmaf(cbv, sc, fmaf(-mean, sc, s_shift[ch]));
-            if (blockIdx.x == 0) {
-                prm.smean[ch] = mean;
-                prm.sinvstd[ch] = invstd;
-                if (prm.rmean) {
-                    const float unbiased = var * (n / fmaxf(n - 1.f, 1.f));
-                    prm.rmean[ch] = (1.f - prm.momentum) * prm.rmean[ch] + prm.momentum * mean;
-                    prm.rvar[ch] = (1.f - prm.momentum) * prm.rvar[ch] + prm.momentum * unbiased;
-                }
+        }
+        // side effects of the channels this CTA owns (same arithmetic as above, so every copy of a statistic is identical)
+        for (int ch = ch_own; ch < C; ch += kThreads * G) {
+            const int ll = ch >> 3, k = ch & 7;
+            const float cbv = ld_bias(prm.cbias1, prm.cbias_dtype, ch) + ld_bias(prm.cbias2, prm.cbias_dtype, ch);
+            const float mean = red[k * L + ll] + cbv;
+            const float var = red[(8 + k) * L + ll];
+            prm.smean[ch] = mean;
+            prm.sinvstd[ch] = 1.0f / sqrtf(var + prm.eps);
+            if (prm.rmean) {
+                const float unbiased = var * (n / fmaxf(n - 1.f, 1.f));
+                const float rm = (ch == ch_own) ? rm_own : prm.rmean[ch];
+                const float rv = (ch == ch_own) ? rv_own : prm.rvar[ch];
+                prm.rmean[ch] = (1.f - prm.momentum) * rm + prm.momentum * mean;
+                prm.rvar[ch] = (1.f - prm.momentum) * rv + prm.momentum * unbiased;
             }
         }
         if (blockIdx.x == 0 && tid == 0 && prm.nbt) *prm.nbt += 1;
     } else {
         for (int ch = tid; ch < C; ch += kThreads) {
-            const float cbv = ld_bias(prm.cbias1, prm.cbias_dtype, ch) + ld_bias(prm.cbias2, prm.cbias_dtype, ch);
+            const float cbv = (ch == tid) ? cb_first : ld_bias(prm.cbias1, prm.cbias_dtype, ch) + ld_bias(prm.cbias2, prm.cbias_dtype, ch);
             const float invstd = 1.0f / sqrtf(prm.rvar[ch] + prm.eps);
             const float sc = invstd * s_scale[ch];
             s_scale[ch] = sc;
@@ -1017,13 +1036,16 @@ __global__ void __launch_bounds__(kBlock, 1) syncbn_bwd_kernel(const __grid_cons
             float mu = s_d[ch];
             if (kFold) {
                 mu -= ld_bias(prm.cbias1, prm.cbias_dtype, ch) + ld_bias(prm.cbias2, prm.cbias_dtype, ch);
-                if (blockIdx.x == 0) {
+                if (ch % static_cast<int>(gridDim.x) == static_cast<int>(blockIdx.x)) {
+                    // (spread over the grid: channel ch belongs to CTA ch % gridDim — CTA 0 alone used to be the last to finish)
                     // Σ_local dz = A (Σ_loc dy_m - n_loc mean_dy) + B Σ_loc (z - mean): the GPU-local totals come from the
-                    // slice owners as packets (same tag), so no fence or barrier is involved
+                    // slice owners as packets (same tag), so no fence or barrier is involved; both are requested together
                     int fail = 0;
                     const unsigned long long to = prm.c.timeout_cycles ? prm.c.timeout_cycles : 4000000000ull;
-                    const float s1 = wait_packet_gpu(prm.w.locpk + (k * L + ll), call_tag(prm.tag, prm.epoch), to, fail);
-                    const float s3 = wait_packet_gpu(prm.w.locpk + ((16 + k) * L + ll), call_tag(prm.tag, prm.epoch), to, fail);
+                    const uint32_t tg = call_tag(prm.tag, prm.epoch);
+                    const uint2 p1 = ld_packet_gpu(prm.w.locpk + (k * L + ll)), p3 = ld_packet_gpu(prm.w.locpk + ((16 + k) * L + ll));
+                    const float s1 = (p1.y == tg) ? __uint_as_float(p1.x) : wait_packet_gpu(prm.w.locpk + (k * L + ll), tg, to, fail);
+                    const float s3 = (p3.y == tg) ? __uint_as_float(p3.x) : wait_packet_gpu(prm.w.locpk + ((16 + k) * L + ll), tg, to, fail);
                     const float db = A * (s1 - static_cast<float>(g.rows) * mean_dy) + B * s3;
                     acc_bias_grad(prm.dcbias1, prm.cbias_dtype, ch, db);
                     acc_bias_grad(prm.dcbias2, prm.cbias_dtype, ch, db);

@@ -50,8 +50,9 @@ def test_train_cli_test_mode_evaluates_a_saved_checkpoint():
     res = subprocess.run([sys.executable, os.path.join(ROOT, "test.py")], cwd=ROOT, env=env, capture_output=True, text=True, timeout=500)
     assert res.returncode == 0, res.stderr[-3000:]
     import ast
-    mine = [ast.literal_eval(l) for l in res.stdout.splitlines() if l.startswith("{'MaxF'")]
-    theirs = [ast.literal_eval(l) for l in out.splitlines() if l.startswith("{'MaxF'")]
+    import re
+    dicts = lambda text: [ast.literal_eval(m) for m in re.findall(r"\{'MaxF'[^}]*\}", text)]     # noqa: E731
+    mine, theirs = dicts(res.stdout), dicts(out)
     assert len(mine) == 6 == len(theirs)
     for a, b in zip(mine, theirs):      # test.py runs the network in fp32 (as the reference's does), train.py's test mode under bf16 autocast
         assert all(abs(a[k] - b[k]) < 3e-2 for k in ("MaxF", "MeanF", "MAE", "SM", "EM")), (a, b)
