@@ -30,6 +30,7 @@
 // world == 1 uses the same packet mechanism for the intra-GPU broadcast, so there is no grid barrier.
 // All CTAs must be co-resident (grid ≤ #SMs, 1 CTA/SM). Every spin is bounded; a timeout sets
 // comm->error_flag and lets the kernel run to completion (outstanding bulk copies must land).
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -1126,7 +1127,12 @@ static int make_geom(int64_t rows, int C, int dtype, int nstream, BnGeom& g, int
     long long cap = dv.sm_count < kMaxGrid ? dv.sm_count : kMaxGrid;
     // hop-1 packets cost strips*2C*8 bytes of traffic: keep that well below the tensor itself
     const long long tensor_bytes = rows * C * g.es;
-    long long by_traffic = tensor_bytes / (4ll * 2 * C * 8);
+    static const long long traffic_div = [] {          // experiment knob (tools/r2_call17.sh): SOD_BN_TRAFFIC_DIV, default 4
+        const char* e = getenv("SOD_BN_TRAFFIC_DIV");
+        const long long v = e ? atoll(e) : 4;
+        return v >= 1 ? v : 4;
+    }();
+    long long by_traffic = tensor_bytes / (traffic_div * 2 * C * 8);
     if (by_traffic < 1) by_traffic = 1;
     if (cap > by_traffic) cap = by_traffic;
     if (strips > cap) strips = cap;
