@@ -1,6 +1,5 @@
 """Parity of the SyncBN kernels (world 1 here; world 2 in test_gpu_multi.py) with the fp64 oracle and with
 torch's own batch_norm autograd."""
-import os
 
 import numpy as np
 import pytest
