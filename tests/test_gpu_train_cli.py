@@ -37,6 +37,19 @@ def test_train_cli_two_gpus_graph():
     assert out.count("Results on the testset(") == 6
 
 
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_train_cli_two_gpus_default_model_cp_res50():
+    """the configuration a plain `python train.py -ng 2` runs (config.py defaults: cp_res50, CUDA graph, uint8 input pipeline,
+    validation + final test), shrunk in size only: the activation-checkpointed model re-runs every SyncBN forward — and its
+    cross-rank exchange — inside backward, all of it captured in the graph"""
+    out = _run(2, {"epoch_num": 2, "synthetic_iters_per_epoch": 3, "batch_size": 8, "print_freq": 1, "save_freq": 1, "val_freq": 2,
+                   "input_size": 128, "output_name": "output_cp2", "synthetic_eval_images": 5}, 29705)
+    assert "End Training" in out and out.count("[I:") == 6
+    assert out.count("Results on the valset(") == 1 and out.count("Results on the testset(") == 6
+    losses = [float(l.split("Cur:")[1].split("|")[0]) for l in out.splitlines() if "Cur:" in l]
+    assert len(losses) == 6 and all(0.1 < v < 5.0 for v in losses)
+
+
 def test_train_cli_test_mode_evaluates_a_saved_checkpoint():
     """resume_mode == "test" (the reference's DEFAULT, config.py:28): load the saved weights, evaluate, exit"""
     common = {"epoch_num": 1, "synthetic_iters_per_epoch": 2, "batch_size": 4, "print_freq": 0, "save_freq": 1, "is_distributed": False,
