@@ -521,6 +521,35 @@ def parity_check(tr, rank: int, world: int) -> dict:
 # ----------------------------------------------------------------------------------------------------
 # ride-along measurements (BASELINE configs 4 and 5, SyncBN exchange cost, same-box stock-torch comparator)
 # ----------------------------------------------------------------------------------------------------
+def extra_pipeline(tr, rank, world, timed, steps=12):
+    """SURVEY §8f.2 measured: the batch leaves the host as uint8 (what the loader's workers produce before ToTensor), is
+    uploaded and pre-processed by `sod_preprocess_batch` one batch ahead on a side stream (`DevicePrefetcher`), and the
+    iteration consumes it — end to end per step: pinned uint8 H2D + pre-processing kernel + iteration + loss D2H."""
+    from distributed_sod_project_b200.pipeline import DevicePrefetcher, preprocess_batch
+    g = torch.Generator().manual_seed(99 + rank)
+    host = [(torch.randint(0, 256, (BS, SIZE, SIZE, 3), generator=g, dtype=torch.uint8).pin_memory(),
+             torch.randint(0, 256, (BS, SIZE, SIZE), generator=g, dtype=torch.uint8).pin_memory(), None) for _ in range(4)]
+    pinned = torch.zeros(1).pin_memory()
+
+    def epoch(n):
+        pre = DevicePrefetcher([host[i % 4] for i in range(n)], size_list=None)
+        for x, m, _ in pre:
+            red, _, _ = tr.forward_backward_update(x, m, report=False)
+            pinned.copy_(red.reshape(1), non_blocking=True)
+
+    epoch(3)
+    ms = timed(lambda i: epoch(steps) if i == 0 else None, 1)
+    img_d, msk_d = host[0][0].cuda(), host[0][1].cuda()
+    for _ in range(3):
+        preprocess_batch(img_d, msk_d)
+    us = timed(lambda i: preprocess_batch(img_d, msk_d), 20) / 20 * 1e3
+    px = BS * SIZE * SIZE
+    return {"value": world * BS * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
+            "h2d_bytes_per_step": 4 * px, "h2d_bytes_per_step_fp32_loader": 16 * px,
+            "preprocess_kernel_us": us, "preprocess_kernel_gbs": 20 * px / (us * 1e-6) / 1e9,
+            "note": "uint8 HWC image + uint8 mask in, normalised channels-last fp32 image + fp32 mask out (20 B/pixel of traffic)"}
+
+
 def extra_multiscale(tr, rank, world, timed, steps=12):
     """BASELINE config 4: multi-scale {256,320,384}, one size per batch (rank-shared RNG), on the trainer that was just
     timed — two more graphs are captured (the 320 one exists), then `steps` iterations are timed like the headline."""
@@ -771,7 +800,8 @@ def run_b200_arm(args):
     if not args.multiscale and not args.no_extras:
         # BASELINE configs 4 and 5 and the same-box comparator ride along with every default run, so that the round-end
         # 1/2/4/8-GPU runs record them too (every rank takes part; a failure here never costs the headline line)
-        for name, fn in (("multiscale", lambda: extra_multiscale(tr, rank, world, timed)),
+        for name, fn in (("input_pipeline", lambda: extra_pipeline(tr, rank, world, timed)),
+                         ("multiscale", lambda: extra_multiscale(tr, rank, world, timed)),
                          ("allreduce_sweep", lambda: extra_sweep(world, timed)),
                          ("syncbn_exchange", lambda: extra_syncbn_exchange(world, timed, dtype)),
                          ("torch_same_box", lambda: extra_torch_arm(args, dtype, rank, world, timed))):
